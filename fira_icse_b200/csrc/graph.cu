@@ -1,0 +1,246 @@
+// GNN message passing: batched CSR build from the reference's dense adjacency, and the
+// gather -> scale -> segmented-reduce ("scatter") kernel that replaces torch.bmm(edge, x)
+// (gnn_transformer.py:80).
+//
+// Adjacency format ("packed edges"): graphs are concatenated in batch order; rows are the
+// destination nodes in (graph b, node i) order, `rowptr` is cumulative over the whole batch,
+// `col` holds LOCAL source-node ids j in [0, N), `val` = A[b, i, j] as fp32 (the reference casts
+// its float64 adjacency with edge.float(), gnn_transformer.py:80).
+//
+// Feature rows live in the encoder's segment-major node buffer: all code rows of all
+// graphs, then all sub-token rows, then all AST/edit rows.  seg_row() maps (b, node) to that row.
+// With n_sub = n_ast = 0 the map is the identity (synthetic single-segment graphs).
+#include "common.cuh"
+#include "fira_b200.h"
+
+namespace {
+
+constexpr int D = 256;
+
+struct Segs { int B, n0, n1, n2; };   // n0 code, n1 sub-token, n2 AST/edit rows per graph
+
+__device__ __forceinline__ long seg_row(const Segs& s, int b, int j) {
+  if (j < s.n0) return (long)b * s.n0 + j;
+  if (j < s.n0 + s.n1) return (long)s.B * s.n0 + (long)b * s.n1 + (j - s.n0);
+  return (long)s.B * (s.n0 + s.n1) + (long)b * s.n2 + (j - s.n0 - s.n1);
+}
+// inverse: segment-major row -> (b, node)
+__device__ __forceinline__ void seg_unrow(const Segs& s, long r, int& b, int& i) {
+  const long e0 = (long)s.B * s.n0, e1 = e0 + (long)s.B * s.n1;
+  if (r < e0) { b = (int)(r / s.n0); i = (int)(r % s.n0); }
+  else if (r < e1) { long q = r - e0; b = (int)(q / s.n1); i = s.n0 + (int)(q % s.n1); }
+  else { long q = r - e1; b = (int)(q / s.n2); i = s.n0 + s.n1 + (int)(q % s.n2); }
+}
+
+// ---------------------------------------------------------------- dense -> CSR
+template <typename E> __device__ __forceinline__ float edge_to_float(E v) { return (float)v; }
+template <> __device__ __forceinline__ float edge_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename E> __device__ __forceinline__ bool edge_nonzero(E v) { return v != (E)0; }
+template <> __device__ __forceinline__ bool edge_nonzero<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v) != 0.f; }
+
+// pass 1: one warp per (b, i): count the non-zeros of A[b, i, :]
+template <typename E>
+__global__ void dense_count_kernel(const E* __restrict__ a, long sb, long si, long sj, int B, int N,
+                                   int* __restrict__ counts) {
+  const long rows = (long)B * N;
+  const int lane = threadIdx.x & 31;
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long)gridDim.x * (blockDim.x >> 5)) {
+    const E* row = a + (r / N) * sb + (r % N) * si;
+    int c = 0;
+    for (int j = lane; j < N; j += 32) c += edge_nonzero(row[(long)j * sj]) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) counts[r] = c;
+  }
+}
+
+// exclusive scan of n counts into rowptr[0..n] by ONE 1024-thread CTA (n = B*650 <= a few 100k)
+__global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ rowptr, long n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long base = 0; base < n; base += 1024) {
+    long i = base + threadIdx.x;
+    int v = i < n ? counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int excl = carry + (warp ? warp_tot[warp - 1] : 0) + x - v;
+    if (i < n) rowptr[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowptr[n] = carry;
+}
+
+// pass 2: same traversal, ballot-compacted writes (columns stay sorted)
+template <typename E>
+__global__ void dense_fill_kernel(const E* __restrict__ a, long sb, long si, long sj, int B, int N,
+                                  const int* __restrict__ rowptr, int* __restrict__ col, float* __restrict__ val) {
+  const long rows = (long)B * N;
+  const int lane = threadIdx.x & 31;
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long)gridDim.x * (blockDim.x >> 5)) {
+    const E* row = a + (r / N) * sb + (r % N) * si;
+    int pos = rowptr[r];
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      E v = j < N ? row[(long)j * sj] : (E)0;
+      const bool nz = j < N && edge_nonzero(v);
+      const unsigned bal = __ballot_sync(0xffffffffu, nz);
+      if (nz) {
+        int o = pos + __popc(bal & ((1u << lane) - 1u));
+        col[o] = j; val[o] = edge_to_float(v);
+      }
+      pos += __popc(bal);
+    }
+  }
+}
+
+__global__ void csr_rowsum_kernel(const int* __restrict__ rowptr, const float* __restrict__ val, Segs s, int N,
+                                  float* __restrict__ out) {
+  const long R = (long)s.B * N;
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long)gridDim.x * blockDim.x) {
+    int b, i; seg_unrow(s, r, b, i);
+    const long g = (long)b * N + i;
+    float t = 0.f;
+    for (int e = rowptr[g]; e < rowptr[g + 1]; ++e) t += val[e];
+    out[r] = t;
+  }
+}
+
+// ---------------------------------------------------------------- the GNN "scatter": Y = A X (+ addend)
+// One warp owns one destination row: 32 lanes x 8 features = the whole 256-wide row, so each
+// neighbour row is ONE fully coalesced 1 KB (fp32) / 512 B (bf16) read; the (col, val) segment of
+// the row is fetched by the lanes in parallel and broadcast by shuffle (segmented reduction with no
+// atomics: CSR is destination-sorted).  fp32 accumulation in source order (deterministic).
+// Algorithmic bytes per pass: 2 * R * D * sizeof(T) + (R + 1) * 4 + nnz * 8   (SURVEY.md section 8d).
+template <typename T>
+__global__ void __launch_bounds__(256) csr_spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                       const float* __restrict__ val, const T* __restrict__ x,
+                                                       const T* __restrict__ addend, T* __restrict__ y, Segs s, int N) {
+  const long R = (long)s.B * N;
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  for (long r = warp0; r < R; r += nwarps) {
+    int b, i; seg_unrow(s, r, b, i);
+    const long g = (long)b * N + i;
+    const int e0 = rowptr[g], e1 = rowptr[g + 1];
+    float acc[8];
+    if (addend) Act<T>::load8(addend + r * D + lane * 8, acc);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int n = min(32, e1 - eb);
+      int c = 0; float w = 0.f;
+      if (lane < n) { c = col[eb + lane]; w = val[eb + lane]; }
+      int t = 0;
+      for (; t + 1 < n; t += 2) {      // two neighbour rows in flight per lane
+        const int c0 = __shfl_sync(0xffffffffu, c, t), c1 = __shfl_sync(0xffffffffu, c, t + 1);
+        const float w0 = __shfl_sync(0xffffffffu, w, t), w1 = __shfl_sync(0xffffffffu, w, t + 1);
+        float v0[8], v1[8];
+        Act<T>::load8(x + seg_row(s, b, c0) * D + lane * 8, v0);
+        Act<T>::load8(x + seg_row(s, b, c1) * D + lane * 8, v1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w1, v1[k], acc[k]);
+      }
+      if (t < n) {
+        const int c0 = __shfl_sync(0xffffffffu, c, t);
+        const float w0 = __shfl_sync(0xffffffffu, w, t);
+        float v0[8];
+        Act<T>::load8(x + seg_row(s, b, c0) * D + lane * 8, v0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
+      }
+    }
+    Act<T>::store8(y + r * D + lane * 8, acc);
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                                            \
+  if ((dtype) == FIRA_F32) { using T = float; __VA_ARGS__ }                               \
+  else if ((dtype) == FIRA_BF16) { using T = __nv_bfloat16; __VA_ARGS__ }                 \
+  else { fira_set_error(FIRA_ERR_DTYPE, "unknown dtype %d", (int)(dtype)); return FIRA_ERR_DTYPE; }
+
+extern "C" {
+
+// edge_dtype: 0 f32, 1 bf16, 2 f64, 3 f16 is not supported (the reference only produces f64/f32)
+int fira_csr_count_dense(const void* edge, int edge_dtype, long stride_b, long stride_i, long stride_j, int B, int N,
+                         int* counts, int* rowptr, void* stream) {
+  FIRA_CHECK_ARG(B > 0 && N > 0, FIRA_ERR_SHAPE, "csr_count_dense: B=%d N=%d", B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long rows = (long)B * N;
+  int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
+  if (edge_dtype == 0) dense_count_kernel<float><<<grid, 256, 0, st>>>((const float*)edge, stride_b, stride_i, stride_j, B, N, counts);
+  else if (edge_dtype == 2) dense_count_kernel<double><<<grid, 256, 0, st>>>((const double*)edge, stride_b, stride_i, stride_j, B, N, counts);
+  else if (edge_dtype == 1) dense_count_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)edge, stride_b, stride_i, stride_j, B, N, counts);
+  else { fira_set_error(FIRA_ERR_DTYPE, "csr_count_dense: edge dtype %d", edge_dtype); return FIRA_ERR_DTYPE; }
+  FIRA_CHECK_LAUNCH("fira_csr_count_dense");
+  scan_kernel<<<1, 1024, 0, st>>>(counts, rowptr, rows);
+  FIRA_CHECK_LAUNCH("fira_csr_count_dense/scan");
+  return FIRA_OK;
+}
+
+int fira_csr_fill_dense(const void* edge, int edge_dtype, long stride_b, long stride_i, long stride_j, int B, int N,
+                        const int* rowptr, int* col, float* val, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long rows = (long)B * N;
+  int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
+  if (edge_dtype == 0) dense_fill_kernel<float><<<grid, 256, 0, st>>>((const float*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
+  else if (edge_dtype == 2) dense_fill_kernel<double><<<grid, 256, 0, st>>>((const double*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
+  else if (edge_dtype == 1) dense_fill_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
+  else { fira_set_error(FIRA_ERR_DTYPE, "csr_fill_dense: edge dtype %d", edge_dtype); return FIRA_ERR_DTYPE; }
+  FIRA_CHECK_LAUNCH("fira_csr_fill_dense");
+  return FIRA_OK;
+}
+
+int fira_csr_rowsum(const int* rowptr, const float* val, int B, int n_code, int n_sub, int n_ast, float* out,
+                    void* stream) {
+  Segs s{B, n_code, n_sub, n_ast};
+  const int N = n_code + n_sub + n_ast;
+  FIRA_CHECK_ARG(n_code > 0 && n_sub >= 0 && n_ast >= 0, FIRA_ERR_SHAPE, "csr_rowsum: segments");
+  const long R = (long)B * N;
+  csr_rowsum_kernel<<<(int)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, val, s, N, out);
+  FIRA_CHECK_LAUNCH("fira_csr_rowsum");
+  return FIRA_OK;
+}
+
+int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, const void* x, const void* addend,
+                       void* y, int B, int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream) {
+  FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "gcn_aggregate: dim %d != 256", dim);
+  FIRA_CHECK_ARG(n_code > 0 && n_sub >= 0 && n_ast >= 0 && B > 0, FIRA_ERR_SHAPE, "gcn_aggregate: segments");
+  FIRA_CHECK_ARG(fira_aligned16(x) && fira_aligned16(y) && fira_aligned16(addend), FIRA_ERR_ALIGN,
+                 "gcn_aggregate: 16-B alignment");
+  FIRA_CHECK_ARG(x != y, FIRA_ERR_ARG, "gcn_aggregate: in-place not supported");
+  Segs s{B, n_code, n_sub, n_ast};
+  const int N = n_code + n_sub + n_ast;
+  const long R = (long)B * N;
+  long ctas = (R + 7) / 8;
+  const long cap = 148L * 8 * 4;           // 8 CTAs of 8 warps per SM, x4 grid-stride waves max
+  int grid = (int)(ctas < cap ? ctas : cap);
+  DISPATCH_T(dtype, csr_spmm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, (const T*)x,
+                                                                                 (const T*)addend, (T*)y, s, N);)
+  FIRA_CHECK_LAUNCH("fira_gcn_aggregate");
+  return FIRA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""`Model.py` surface of the reference (CopyNet, TransModel) on the B200 CUDA path.
+
+    model = TransModel(args)                  # args as run_model.py:27-56
+    loss_sum, n_tok = model(sou, tar, attr, mark, ast_change, edge, tar_label, sub_token, 'train')
+    ids = model(..., 'dev')                   # argmax over the 25,020-wide dual-copy distribution
+
+`edge` is the reference's dense [B,650,650] float tensor (any float dtype) OR a
+fira_icse_b200.graph.PackedEdges (what the packed loader emits).  Sub-modules `encoder`,
+`decoder`, `out_fc`, `copy_net` are individually callable, as the reference's beam loop
+requires (run_model.py:204,256,257,259).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import Decoder, Encoder, _i32, _u8
+
+
+class _OutFc(nn.Linear):
+    """nn.Linear whose forward runs on fira_gemm_f32 (Model.py:34,54)."""
+
+    def forward(self, x):
+        return ops.LinearFn.apply(x, self.weight, self.bias)
+
+
+class CopyNet(nn.Module):
+    """Model.py:7-20.  forward(source, target) -> (pointer scores [B,T,S], gate [B,T,2])."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.embedding_size = args.embedding_dim
+        self.LinearSource = nn.Linear(self.embedding_size, self.embedding_size, bias=False)
+        self.LinearTarget = nn.Linear(self.embedding_size, self.embedding_size, bias=False)
+        self.LinearRes = nn.Linear(self.embedding_size, 1)
+        self.LinearProb = nn.Linear(self.embedding_size, 2)
+
+    def flat_params(self):
+        return [self.LinearSource.weight, self.LinearTarget.weight, self.LinearRes.weight, self.LinearRes.bias,
+                self.LinearProb.weight, self.LinearProb.bias]
+
+    def forward(self, source, traget):
+        scores = ops.CopyScoresFn.apply(source, traget, self.LinearSource.weight, self.LinearTarget.weight,
+                                        self.LinearRes.weight, self.LinearRes.bias)
+        gate_logits = ops.LinearFn.apply(traget, self.LinearProb.weight, self.LinearProb.bias)
+        # [B,T,2] two-way softmax: 60 floats per commit, not worth a kernel outside the fused head
+        return scores, torch.softmax(gate_logits, dim=-1)
+
+
+class TransModel(nn.Module):
+    """Model.py:24-86."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.embedding_dim = args.embedding_dim
+        self.vocab_size = args.vocab_size
+        self.sou_len = args.sou_len
+        self.sub_token_len = args.sub_token_len
+        self.encoder = Encoder(args, pad_token_id=0)
+        self.decoder = Decoder(args, pad_token_id=0)
+        self.out_fc = _OutFc(args.embedding_dim, args.vocab_size)
+        self.gate_fc = nn.Linear(args.embedding_dim, 1)   # dead upstream too (Model.py:35)
+        self.copy_net = CopyNet(args)
+
+    def dead_parameters(self):
+        return self.encoder.dead_parameters() + list(self.gate_fc.parameters())
+
+    def live_parameters(self):
+        dead = {id(p) for p in self.dead_parameters()}
+        return [p for p in self.parameters() if id(p) not in dead]
+
+    @staticmethod
+    def shifted_label(tar_label):
+        """Model.py:71-79: labels shifted left by one with a trailing 0."""
+        pad = torch.zeros((tar_label.shape[0], 1), dtype=tar_label.dtype, device=tar_label.device)
+        return torch.cat((tar_label[:, 1:], pad), dim=1)
+
+    def forward(self, sou, tar, attr, mark, ast_change, edge, tar_label, sub_token, stage="train"):
+        dev = self.out_fc.weight.device
+        sou, tar, mark, ast_change, tar_label, sub_token = (
+            t.to(dev, non_blocking=True) for t in (sou, tar, mark, ast_change, tar_label, sub_token))
+        mem_mask = torch.cat((sou != 0, sub_token != 0), dim=1)
+        memory = self.encoder.encode_memory(sou, mark, ast_change, edge, sub_token)
+        dec = self.decoder(tar, memory, mem_mask, tar != 0)
+        label = self.shifted_label(tar_label)
+        want_ids = stage != "train"
+        loss_sum, _, ids = ops.HeadFn.apply(want_ids, memory, dec, _u8(mem_mask), _i32(label).view(-1),
+                                            self.out_fc.weight, self.out_fc.bias, *self.copy_net.flat_params())
+        if stage == "train":
+            return loss_sum, (label != 0).sum()
+        elif stage == "dev" or stage == "test":
+            return ids.long()
+        raise ValueError(f"unknown stage {stage!r}")

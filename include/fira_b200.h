@@ -1,0 +1,138 @@
+/* libfira_b200 -- C ABI of the B200-native FIRA hot path.
+ *
+ * The reference (DJjjjhao/FIRA-ICSE) has no FFI of its own: its hot path is PyTorch library
+ * calls issued from Model.py / gnn_transformer.py / combination_layer.py.  The drop-in boundary
+ * is therefore the nn.Module surface (kept by fira_icse_b200/), and THIS header is the thin
+ * C ABI those modules call instead of torch ops.  Each entry point names the reference
+ * statement(s) it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory owned by the caller (PyTorch caching
+ *     allocator); the library never allocates, frees or retains a pointer;
+ *   - tensors are contiguous row-major unless a leading dimension (ld*) is given, 16-byte aligned;
+ *   - ids / indices are int32; masks are uint8 (1 = keep);
+ *   - `dtype` selects the ACTIVATION storage type: FIRA_F32 (parity mode) or FIRA_BF16 (throughput
+ *     mode); parameters, statistics and gradients of parameters are always fp32;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no implicit sync;
+ *   - return 0 on success, a FIRA_ERR_* code otherwise; fira_last_error_string() describes the last
+ *     failure on the calling thread; nothing throws or aborts across the boundary;
+ *   - re-entrant, no hidden global state besides the per-thread error string;
+ *   - dropout masks are a pure function of (seed, stream_id, element index): backward recomputes them.
+ */
+#ifndef FIRA_B200_H_
+#define FIRA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIRA_F32 0
+#define FIRA_BF16 1
+#define FIRA_EDGE_F32 0
+#define FIRA_EDGE_BF16 1
+#define FIRA_EDGE_F64 2
+
+int fira_version(void);                    /* ABI version, bumped on any signature change */
+const char* fira_last_error_string(void);
+int fira_built_arch(void);                 /* 100 when compiled for sm_100a */
+
+/* ---- generic fp32 Linear pieces (every nn.Linear of the path; e.g. gnn_transformer.py:78,82,
+ *      141-143,158,171-173,200-204; Model.py:16-19,54).
+ *      C[M,N] = A(MxK) * B(KxN) + bias[n] + rs[m]*rc[n], optional relu.
+ *      A(m,k) = a_kcontig ? A[m*lda+k] : A[k*lda+m];  B(k,n) = b_kcontig ? B[n*ldb+k] : B[k*ldb+n].
+ *      accumulate: C += result.  splits>1: K is split across CTAs, partials are atomically added
+ *      (the library zero-fills C first unless accumulate). */
+int fira_gemm_f32(const float* A, long lda, int a_kcontig, const float* B, long ldb, int b_kcontig, float* C,
+                  long ldc, int M, int N, int K, const float* bias, const float* rs, const float* rc, int relu,
+                  int accumulate, int splits, void* stream);
+
+/* ---- embeddings -------------------------------------------------------------------------------
+ * Encoder node features in segment-major order (all code rows, all sub-token rows, all AST/edit
+ * rows): emb[sou]+PE | emb[sub_token] | ast_emb[ast_change]     (gnn_transformer.py:46-52,58).
+ * out_code holds rows [0, B*n_code); out_rest is indexed by the GLOBAL row (rows >= B*n_code). */
+int fira_embed_nodes_fwd(const int* sou, const int* sub_token, const int* ast_change, const float* emb,
+                         const float* ast_emb, const float* pos_table, void* out_code, void* out_rest, int B,
+                         int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream);
+int fira_embed_nodes_bwd(const int* sou, const int* sub_token, const int* ast_change, const void* d_code,
+                         const void* d_rest, float* d_emb, float* d_ast_emb, int B, int n_code, int n_sub, int n_ast,
+                         int dim, int dtype, void* stream);
+/* Decoder input: dec_emb[tar] + PE[t]  (gnn_transformer.py:110-113). */
+int fira_embed_rows_fwd(const int* ids, const float* emb, const float* pos_table, void* out, long rows, int period,
+                        int dim, int dtype, void* stream);
+int fira_embed_rows_bwd(const int* ids, const void* d_out, float* d_emb, long rows, int dim, int dtype, void* stream);
+
+/* ---- LN(dropout(z) + resid)  (gnn_transformer.py:83,161,174,205) -------------------------------
+ * rows < split are written to outA[row], the others to outB[row] (lets a GCN layer hand its code
+ * rows to the next Combination without a torch.cat / slice copy). */
+int fira_ln_residual_fwd(const void* z, const void* resid, const float* gamma, const float* beta, void* outA,
+                         void* outB, long split, float* mean, float* rstd, long rows, int dim, float p_drop,
+                         uint64_t seed, uint32_t stream_id, int dtype, void* stream);
+int fira_ln_residual_bwd(const void* d_outA, const void* d_outB, long split, const void* z, const void* resid,
+                         const float* mean, const float* rstd, const float* gamma, void* d_z, void* d_resid,
+                         int d_resid_accum, float* d_gamma, float* d_beta, long rows, int dim, float p_drop,
+                         uint64_t seed, uint32_t stream_id, int dtype, void* stream);
+
+/* ---- Combination gate (combination_layer.py:7-17): c = v + sigmoid(q*(k-v)/sqrt(d_head))*(k-v),
+ *      dropout; qk = [q | k] per row, v = vtab[mark[row]] (4 x dim table = Linear(mark_embedding)). */
+int fira_comb_gate_fwd(const void* qk, long ld_qk, const float* vtab, const int* mark, void* out, long rows, int dim,
+                       int d_head, float p_drop, uint64_t seed, uint32_t stream_id, int dtype, void* stream);
+int fira_comb_gate_bwd(const void* qk, long ld_qk, const float* vtab, const int* mark, const void* d_out, void* d_qk,
+                       float* d_vtab, long rows, int dim, int d_head, float p_drop, uint64_t seed, uint32_t stream_id,
+                       int dtype, void* stream);
+
+/* d[i] = h[i] > 0 ? d[i] : 0  (backward of the FeedForward relu, gnn_transformer.py:172). */
+int fira_relu_bwd(const void* h, void* d, long n, int dtype, void* stream);
+/* out[n] += sum_m w[m] * x[m,n]  (w == NULL -> 1): bias gradients. */
+int fira_colsum(const void* x, long ld, long M, int N, const float* row_weight, float* out, int dtype, void* stream);
+
+/* memory = cat(code rows, sub-token rows) per commit (Model.py:48) and its adjoint. */
+int fira_pack_memory(const void* code, const void* rest, void* mem, int B, int n_code, int n_sub, int dim, int dtype,
+                     void* stream);
+int fira_unpack_memory(const void* d_mem, void* d_code, void* d_rest, int B, int n_code, int n_sub, int n_ast, int dim,
+                       int dtype, void* stream);
+
+/* ---- graph: dense [B,N,N] adjacency (Dataset.py:340 toarray(), any strides) -> packed CSR.
+ * Two calls because the caller owns the buffers: count (+ exclusive scan into rowptr[B*N+1]),
+ * read rowptr[B*N] to size col/val, then fill. */
+int fira_csr_count_dense(const void* edge, int edge_dtype, long stride_b, long stride_i, long stride_j, int B, int N,
+                         int* counts, int* rowptr, void* stream);
+int fira_csr_fill_dense(const void* edge, int edge_dtype, long stride_b, long stride_i, long stride_j, int B, int N,
+                        const int* rowptr, int* col, float* val, void* stream);
+int fira_csr_rowsum(const int* rowptr, const float* val, int B, int n_code, int n_sub, int n_ast, float* out,
+                    void* stream);
+/* The GNN scatter: y = A x (+ addend), replacing torch.bmm(edge.float(), x) (gnn_transformer.py:80). */
+int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, const void* x, const void* addend,
+                       void* y, int B, int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream);
+
+/* ---- attention core (gnn_transformer.py:144-156); stats = (row max, row sum) [B,H,Lq,2]. */
+int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                  const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
+                  int Lk, int d_head, int dtype, void* stream);
+int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                  const unsigned char* key_mask, int causal, const void* d_ctx, long ldo, const float* stats, void* dq,
+                  long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H, int Lq, int Lk, int d_head,
+                  int dtype, void* stream);
+
+/* ---- CopyNet scores (Model.py:17-18): sc[b,t,s] = b_res + w_res . tanh(src[b,s] + tgt[b,t]). */
+int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res, float* scores,
+                         int B, int T_len, int S, int dim, int dtype, void* stream);
+int fira_copy_scores_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
+                         const unsigned char* row_active, void* d_src_proj, float* d_tgt_proj, float* d_w_res,
+                         float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream);
+
+/* ---- dual-copy mixture, loss and argmax (Model.py:54-86).  stats: 8 floats per row
+ *      (vmax, vsum, cmax, csum, g0, g1, p_label, 0).  argmax_out may be NULL (training). */
+int fira_pointer_mix_nll_fwd(const void* logits, long ld_logits, const float* copy_scores, const float* gate_logits,
+                             const unsigned char* mem_mask, const int* label, float* stats, float* nll,
+                             int* argmax_out, long rows, int T_len, int V, int S, int dtype, void* stream);
+int fira_pointer_mix_nll_bwd(const void* logits, long ld_logits, const float* copy_scores,
+                             const unsigned char* mem_mask, const int* label, const float* stats,
+                             const float* upstream, void* d_logits, float* d_copy_scores, float* d_gate_logits,
+                             unsigned char* row_active, long rows, int T_len, int V, int S, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIRA_B200_H_ */
