@@ -126,7 +126,12 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_kernel(AttnArgs a, const
       delta = fmaf(p, dp, delta);
     }
     delta = warp_sum(delta);
-    for (int s = lane; s < a.Lk; s += 32) Sm[t * LkP + s] = Pm[t * LkP + s] * (Sm[t * LkP + s] - delta);
+    // masked_fill overwrote the masked scores: no gradient reaches them even when P != 0 there
+    // (a fully masked row has uniform P)
+    for (int s = lane; s < a.Lk; s += 32) {
+      const bool ok = km[s] && (!a.causal || s <= t);
+      Sm[t * LkP + s] = ok ? Pm[t * LkP + s] * (Sm[t * LkP + s] - delta) : 0.f;
+    }
     __syncwarp();
     float g = 0.f;   // dQ[t][lane]
     for (int s = 0; s < a.Lk; ++s) g = fmaf(Sm[t * LkP + s], Ks[s * KPAD + lane], g);

@@ -1,0 +1,164 @@
+"""Whole-path parity on the B200: the CUDA TransModel against (a) the committed outputs of the
+unmodified reference (tests/golden/model_first128.npz) and (b) the CPU oracle, on real DataSet
+commits; fp32 parity mode, tolerance 1e-4 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from fira_testlib import golden_batch, load_model_golden, seeded_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def model():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import copy
+    m = copy.deepcopy(seeded_model()).to(DEV)
+    m.eval()
+    return m
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_model_golden()
+
+
+def to_dev(batch):
+    return [b.to(DEV) if torch.is_tensor(b) else b for b in batch]
+
+
+def test_state_dict_is_the_reference_layout(model, gold):
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(k) for k in gold["param_keys"]]
+    s = np.array([sd[k].double().sum().item() for k in sd])
+    np.testing.assert_allclose(s, gold["param_sum"], rtol=0, atol=1e-9)
+
+
+def test_forward_matches_reference_on_128_commits(model, gold):
+    bs = int(gold["batch_size"])
+    for bi, lo in enumerate(range(0, 128, bs)):
+        batch = to_dev(golden_batch(lo, lo + bs))
+        with torch.no_grad():
+            loss_sum, n_tok = model(*batch, "train")
+            ids = model(*batch, "dev")
+        assert int(n_tok) == int(gold["mask_sums"][bi])
+        assert abs(loss_sum.item() - gold["loss_sums"][bi]) <= RTOL * gold["loss_sums"][bi]
+        assert np.array_equal(ids.cpu().numpy(), gold["dev_ids"][lo:lo + bs]), "argmax ids differ from the reference"
+
+
+def test_intermediates_match_reference(model, gold):
+    from fira_icse_b200 import ops
+    batch = to_dev(golden_batch(0, 8))
+    sou, tar, attr, mark, ast_change, edge, tar_label, sub_token = batch
+    with torch.no_grad():
+        code, sub = model.encoder(sou, sou != 0, attr, mark, ast_change, edge, sub_token)
+        assert code.shape == (8, 210, 256) and sub.shape == (8, 160, 256)
+        memory = torch.cat((code, sub), 1)
+        mem_mask = torch.cat((sou != 0, sub_token != 0), 1)
+        dec = model.decoder(tar, memory, mem_mask, tar != 0)
+        logits = model.out_fc(dec)
+        scores, gate = model.copy_net(memory, dec)
+        _, nll, _ = ops.HeadFn.apply(False, memory, dec, mem_mask.to(torch.uint8),
+                                     model.shifted_label(tar_label).to(torch.int32).view(-1),
+                                     model.out_fc.weight, model.out_fc.bias, *model.copy_net.flat_params())
+    real = mem_mask[:4].unsqueeze(-1).cpu().numpy()
+    # padding rows are compared too: the dense-row path reproduces them exactly like the reference
+    np.testing.assert_allclose(memory[:4].cpu().numpy(), gold["full_memory"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(memory[:4].cpu().numpy() * real, gold["full_memory"] * real, rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(dec[:4].cpu().numpy(), gold["full_decoder"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(scores[:4].cpu().numpy(), gold["full_copy"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(gate[:4].cpu().numpy(), gold["full_gate"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(logits[:4, :, :256].cpu().numpy(), gold["full_logits_head"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(nll.cpu().numpy(), gold["nll"][:8], rtol=RTOL, atol=1e-5)
+
+
+def test_packed_edges_equal_dense_edges(model):
+    from fira_icse_b200 import PackedEdges
+    dense = to_dev(golden_batch(0, 6))
+    packed = list(dense)
+    packed[5] = PackedEdges.from_coo_lists(golden_batch(0, 6, dense_edge=False)[5], 650, DEV)
+    f32 = list(dense)
+    f32[5] = dense[5].float()
+    with torch.no_grad():
+        a = model(*dense, "train")[0].item()
+        b = model(*packed, "train")[0].item()
+        c = model(*f32, "train")[0].item()
+    assert a == b == c
+
+
+def test_gradients_match_reference(model, gold):
+    n = int(gold["grad_commits"])
+    model.zero_grad(set_to_none=True)
+    loss_sum, n_tok = model(*to_dev(golden_batch(0, n)), "train")
+    loss = loss_sum / n_tok
+    loss.backward()
+    assert abs(loss.item() - float(gold["grad_loss"])) <= RTOL * float(gold["grad_loss"])
+    params = dict(model.named_parameters())
+    keys = [str(k) for k in gold["grad_keys"]]
+    assert sorted(k for k, p in params.items() if p.grad is not None) == sorted(keys)
+    worst = 0.0
+    for j, k in enumerate(keys):
+        g = params[k].grad
+        ref = float(gold["grad_norm"][j])
+        err = abs(g.double().norm().item() - ref) / max(ref, 1e-12)
+        worst = max(worst, err)
+        assert err <= 5e-4, (k, err)
+        flat = g.flatten()
+        idx = torch.linspace(0, flat.numel() - 1, 32).long().to(DEV)
+        np.testing.assert_allclose(flat[idx].cpu().numpy(), gold["grad_samples"][j], rtol=5e-3,
+                                   atol=1e-7 + 5e-4 * ref, err_msg=k)
+    for k in gold.files:
+        if k.startswith("gradfull::"):
+            name = k.split("::", 1)[1]
+            np.testing.assert_allclose(params[name].grad.cpu().numpy(), gold[k], rtol=5e-3,
+                                       atol=1e-7 + 5e-4 * float(np.abs(gold[k]).max()), err_msg=name)
+    print("worst grad-norm rel err", worst)
+
+
+def test_matches_cpu_oracle_on_other_commits(model):
+    import fira_oracle as O
+    batch = golden_batch(100, 108)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        detail = {}
+        ref_sum, ref_tok = O.forward(sd, *batch, stage="train", detail=detail)
+        ref_ids = O.forward(sd, *batch, stage="dev")
+        loss_sum, n_tok = model(*to_dev(batch), "train")
+        ids = model(*to_dev(batch), "dev")
+    assert int(n_tok) == int(ref_tok)
+    assert abs(loss_sum.item() - ref_sum.item()) <= RTOL * ref_sum.item()
+    assert torch.equal(ids.cpu(), ref_ids)
+
+
+def test_training_steps_reduce_loss_with_dropout(model):
+    import copy
+    m = copy.deepcopy(model)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    batch = to_dev(golden_batch(32, 48))
+    losses = []
+    for _ in range(6):
+        loss_sum, n_tok = m(*batch, "train")
+        loss = loss_sum / n_tok
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+    # dead blocks never receive gradients
+    assert all(p.grad is None for p in m.dead_parameters())
+    assert all(p.grad is not None for p in m.live_parameters())
+
+
+def test_empty_and_ragged_inputs(model):
+    """all-padding message, batch of one, shortest commit"""
+    b = to_dev(golden_batch(5, 6))
+    b[1] = torch.zeros_like(b[1]); b[6] = torch.zeros_like(b[6])
+    with torch.no_grad():
+        loss_sum, n_tok = model(*b, "train")
+    assert int(n_tok) == 0 and loss_sum.item() == 0.0
