@@ -87,7 +87,8 @@ def test_packed_edges_equal_dense_edges(model):
         a = model(*dense, "train")[0].item()
         b = model(*packed, "train")[0].item()
         c = model(*f32, "train")[0].item()
-    assert a == b == c
+    # split-K partial sums are combined with atomics: equal up to fp32 summation order
+    assert abs(a - b) <= 2e-6 * abs(a) and abs(a - c) <= 2e-6 * abs(a)
 
 
 def test_gradients_match_reference(model, gold):
@@ -104,7 +105,12 @@ def test_gradients_match_reference(model, gold):
     for j, k in enumerate(keys):
         g = params[k].grad
         ref = float(gold["grad_norm"][j])
-        err = abs(g.double().norm().item() - ref) / max(ref, 1e-12)
+        if ref < 1e-7:
+            # softmax shift-invariance makes d/d(fc_k.bias) and d/d(LinearRes.bias) exactly zero in
+            # exact arithmetic: the reference value is round-off noise (~1e-10), only smallness is checked
+            assert g.double().norm().item() < 1e-6, k
+            continue
+        err = abs(g.double().norm().item() - ref) / ref
         worst = max(worst, err)
         assert err <= 5e-4, (k, err)
         flat = g.flatten()
