@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the FIRA hot path: commits/s of one TRAINING step (forward + backward + Adam) on
+synthetic commits that follow the DataSet's node/edge distribution (BASELINE.json metric, config
+"run_model.py train, 1xB200, batch 64"; N GPUs -> global batch 64*N, weak scaling).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the
+same step through the public TransModel.forward API with pinned HOST buffers (H2D of the batch and a
+D2H read of the loss inside the timed region).  `roofline` is the GNN scatter kernel
+(fira_gcn_aggregate) timed live with CUDA events against the measured HBM peak; `cpu_baseline` is
+the CPU oracle port (oracle/fira_oracle.py, the reference algorithm as the reference executes it)
+timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 64
+VOCAB, AST_VOCAB = 24650, 71
+N_POOL = 4                      # distinct synthetic batches rotated through the timed region
+REF_BATCH = 16                  # commits per step of the CPU reference arm (bounded sample)
+
+
+class DotDict(dict):
+    def __getattr__(self, k):
+        return self[k]
+
+
+def model_args():
+    return DotDict(sou_len=210, tar_len=30, att_len=25, ast_change_len=280, sub_token_len=160, lr=1e-4,
+                   dropout_rate=0.1, num_head=8, embedding_dim=256, vocab_size=VOCAB,
+                   ast_change_vocab_size=AST_VOCAB)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 2 + j and r[2 + j].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ data
+def host_batch(first_index, batch_size, pin):
+    """One collated synthetic batch on the host: int64 id tensors + packed CSR (what a loader delivers)."""
+    import torch
+    from fira_icse_b200.graph import PackedEdges
+    from fira_icse_b200.synth import N_NODES, synth_batch
+    ids, coo = synth_batch(first_index, batch_size, VOCAB, AST_VOCAB)
+    t = {k: torch.from_numpy(v) for k, v in ids.items()}
+    t["attr"] = torch.zeros(batch_size, 1, dtype=torch.int64)    # accepted and ignored by the model (Model.py:38)
+    rowptr, col, val = PackedEdges.pack_host(coo, N_NODES, pin=False)
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+        rowptr, col, val = rowptr.pin_memory(), col.pin_memory(), val.pin_memory()
+    return t, (rowptr, col, val), coo
+
+
+def device_batch(hb, dev, B):
+    import torch
+    from fira_icse_b200.graph import PackedEdges
+    from fira_icse_b200.synth import N_NODES
+    t, (rowptr, col, val), _ = hb
+    d = {k: v.to(dev, non_blocking=True) for k, v in t.items()}
+    edges = PackedEdges.from_host(rowptr, col, val, B, N_NODES, dev)
+    return [d["sou"], d["tar"], d["attr"], d["mark"], d["ast_change"], edges, d["tar_label"], d["sub_token"]]
+
+
+def h2d_bytes(hb):
+    t, csr, _ = hb
+    return sum(v.numel() * v.element_size() for v in t.values()) + sum(v.numel() * v.element_size() for v in csr)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_step_fn(batch_size, threads):
+    """Reference-algorithm training step on the host (oracle port: dense 650x650 fp64 adjacency bmm,
+    materialised copy tensor, Adam) -- run_model.py:101-109."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fira_oracle as O
+    torch.set_num_threads(threads)
+    params = {k: v.requires_grad_(True) for k, v in O.random_state_dict(VOCAB, AST_VOCAB).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    pool = []
+    for i in range(2):
+        t, _, coo = host_batch(10_000 + i * batch_size, batch_size, pin=False)
+        edge = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo])     # fp64 [B,650,650] like Dataset.py:340
+        pool.append([t["sou"], t["tar"], t["attr"], t["mark"], t["ast_change"], edge, t["tar_label"], t["sub_token"]])
+    state = {"i": 0}
+
+    def step():
+        b = pool[state["i"] % len(pool)]
+        state["i"] += 1
+        return O.train_step(params, opt, b)
+    return step
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = cpu_threads()
+    step = oracle_step_fn(REF_BATCH, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = REF_BATCH * args.steps / dt
+    line = {"impl": "reference", "metric": "train_commits_per_sec", "value": value, "unit": "commits/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "run_model.py train, synthetic DataSet-like commits, reference algorithm on CPU",
+                       "per_step_batch": REF_BATCH},
+            "cpu_baseline": {"value": value, "unit": "commits/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} training steps of {REF_BATCH} commits (oracle/fira_oracle.py)"},
+            "e2e": {"value": value, "unit": "commits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ roofline
+def spmm_roofline(dev, hb, B):
+    """Time fira_gcn_aggregate alone (CUDA events on the launching stream), cold L2: the launches rotate
+    through buffer pairs whose total size exceeds the 126 MB L2."""
+    import torch
+    from fira_icse_b200 import _lib
+    from fira_icse_b200.graph import PackedEdges
+    from fira_icse_b200.synth import N_CODE, N_SUB, N_AST, N_NODES
+    _, (rowptr, col, val), _ = hb
+    pe = PackedEdges.from_host(rowptr, col, val, B, N_NODES, dev)
+    R = B * N_NODES
+    n_pairs = max(3, int(400e6 // (2 * R * 256 * 4)) + 1)
+    xs = [torch.randn(R, 256, device=dev) for _ in range(n_pairs)]
+    ys = [torch.empty(R, 256, device=dev) for _ in range(n_pairs)]
+    st = torch.cuda.current_stream()
+
+    def launch(i):
+        _lib.call("fira_gcn_aggregate", pe.rowptr.data_ptr(), pe.col.data_ptr(), pe.val.data_ptr(),
+                  xs[i % n_pairs].data_ptr(), None, ys[i % n_pairs].data_ptr(), B, N_CODE, N_SUB, N_AST, 256, 0,
+                  st.cuda_stream)
+    for i in range(6):
+        launch(i)
+    iters = 40
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for i in range(iters):
+        ev[i][0].record(st)
+        launch(i)
+        ev[i][1].record(st)
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    avg_ms = sum(ms) / len(ms)
+    alg_bytes = 2 * R * 256 * 4 + (R + 1) * 4 + pe.nnz * 8          # SURVEY.md section 8d formula, fp32
+    peak, how = measured_peaks()
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("fira_gcn_aggregate_dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": "csr_spmm_kernel<float> (fira_gcn_aggregate)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "median_launch_ms": ms[len(ms) // 2],
+            "launches_timed": iters, "rows": R, "nnz": pe.nnz, "peak_source": how,
+            "l2": f"cold: {n_pairs} rotating buffer pairs ({n_pairs * 2 * R * 1024 / 1e6:.0f} MB > 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path "
+                         "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import fira_icse_b200 as F
+    from fira_icse_b200 import _lib
+    from fira_icse_b200.parallel import DataParallelStep
+
+    B = PER_GPU_BATCH
+    torch.manual_seed(0)
+    model = F.TransModel(model_args()).to(dev)
+    model.train()
+    dp = DataParallelStep(model, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True))
+
+    # every rank gets its own shard of the synthetic stream (graphs shard by commit, no data collective)
+    pool_host = [host_batch((rank * N_POOL + i) * B, B, pin=True) for i in range(N_POOL)]
+    pool_dev = [device_batch(hb, dev, B) for hb in pool_host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident arm ("value")
+    def resident_step(i):
+        dp.step(pool_dev[i % N_POOL])
+    for i in range(args.warmup):
+        resident_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCH_COUNT
+    ms = timed(resident_step, args.steps)
+    launches = _lib.LAUNCH_COUNT - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host batch -> H2D -> TransModel.forward -> backward -> Adam -> loss D2H
+    last_loss = [0.0]
+
+    def e2e_step(i):
+        batch = device_batch(pool_host[i % N_POOL], dev, B)
+        loss, _ = dp.step(batch)
+        last_loss[0] = loss.item()                     # D2H read of the step's result
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- the reference-facing call with the reference's own input format: dense fp64 adjacency on the host
+    dense_info = None
+    if rank == 0 and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import fira_oracle as O
+        t, _, coo = pool_host[0]
+        dense = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo]).pin_memory()    # test-infra helper only
+                                                                                            # builds the INPUT
+        def dense_step(i):
+            d = {k: v.to(dev, non_blocking=True) for k, v in t.items()}
+            loss, _ = dp.step([d["sou"], d["tar"], d["attr"], d["mark"], d["ast_change"],
+                               dense.to(dev, non_blocking=True), d["tar_label"], d["sub_token"]])
+            last_loss[0] = loss.item()
+        dense_step(0)
+        k = min(args.steps, 5)
+        ms_d = timed(dense_step, k)
+        dense_info = {"value": B * k / (ms_d * 1e-3), "unit": "commits/s",
+                      "h2d_bytes_per_step": int(dense.numel() * 8 + sum(v.numel() * 8 for v in t.values())),
+                      "note": "edge passed as the reference's dense float64 [B,650,650] host tensor (Dataset.py:340)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    roof = spmm_roofline(dev, pool_host[0], B)
+
+    # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of 16 commits)
+    threads = cpu_threads()
+    step = oracle_step_fn(REF_BATCH, threads)
+    step()
+    t0 = time.perf_counter()
+    n_cpu = 2
+    for _ in range(n_cpu):
+        step()
+    cpu_dt = time.perf_counter() - t0
+    cpu_value = REF_BATCH * n_cpu / cpu_dt
+
+    line = {"metric": "train_commits_per_sec", "value": value, "unit": "commits/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "run_model.py train, 1xB200 per-GPU batch 64 (BASELINE.json configs[1]), "
+                                   "synthetic commits with the DataSet node/edge distribution",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "precision_mode": "fp32 parity (fp32 storage, fp32 FFMA accumulate)",
+                       "optimizer": "Adam lr 1e-4 (torch fused), dropout on (0.1 / GCN 0.2)",
+                       "l2": f"{N_POOL} distinct batches rotated; one step touches >1 GB of activations (> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "commits/s", "h2d_bytes_per_step": int(h2d_bytes(pool_host[0])),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "api": "TransModel.forward(sou,tar,attr,mark,ast_change,PackedEdges,tar_label,sub_token,'train')"},
+            "e2e_dense_edge": dense_info,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "cpu_baseline": {"value": cpu_value, "unit": "commits/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_cpu} training steps of {REF_BATCH} commits after 1 warm-up "
+                                       "(oracle/fira_oracle.py: dense fp64 adjacency bmm, Adam)"},
+            "last_loss": last_loss[0]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

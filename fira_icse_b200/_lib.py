@@ -70,5 +70,10 @@ def check(rc, what=""):
         raise FiraLibraryError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
 
 
+LAUNCH_COUNT = 0     # C-ABI calls that enqueue GPU work (bench.py reports it as `gpu_launches`)
+
+
 def call(name, *args):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
     check(getattr(lib(), name)(*args), name)

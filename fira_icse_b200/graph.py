@@ -98,6 +98,20 @@ class PackedEdges:
     def from_coo_lists(cls, graphs, N, device, symmetric=True, pin=False):
         """graphs: list of (row, col, val) array-likes, one per commit, local node ids.
         Duplicates are summed (scipy `toarray()` semantics, Dataset.py:294,340)."""
+        rowptr, col, val = cls.pack_host(graphs, N, pin=pin)
+        return cls.from_host(rowptr, col, val, len(graphs), N, device, symmetric)
+
+    @classmethod
+    def from_host(cls, rowptr, col, val, B, N, device, symmetric=True):
+        """Host (ideally pinned) CSR arrays -> device; three async H2D copies, nothing else."""
+        dev = torch.device(device)
+        nb = dev.type == "cuda"
+        return cls(rowptr.to(dev, non_blocking=nb), col.to(dev, non_blocking=nb), val.to(dev, non_blocking=nb),
+                   B, N, symmetric)
+
+    @staticmethod
+    def pack_host(graphs, N, pin=False):
+        """Collate step of the packed loader: per-commit COO -> batched CSR host tensors."""
         rp, cs, vs = [np.zeros(1, np.int64)], [], []
         base = 0
         for row, col, val in graphs:
@@ -117,10 +131,7 @@ class PackedEdges:
         val = torch.from_numpy(np.concatenate(vs) if vs else np.zeros(0, np.float32))
         if pin:
             rowptr, col, val = rowptr.pin_memory(), col.pin_memory(), val.pin_memory()
-        dev = torch.device(device)
-        nb = dev.type == "cuda"
-        return cls(rowptr.to(dev, non_blocking=nb), col.to(dev, non_blocking=nb), val.to(dev, non_blocking=nb),
-                   len(graphs), N, symmetric)
+        return rowptr, col, val
 
     def to_dense(self, dtype=torch.float64):
         """Host-side expansion (tests only)."""

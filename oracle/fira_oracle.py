@@ -191,6 +191,50 @@ def dense_adjacency(rows, cols, vals, n=650, dtype=torch.float64):
     return a
 
 
+def random_state_dict(vocab_size=24650, ast_vocab_size=71, dim=256, seed=0):
+    """Reference-shaped parameters (the live ones of SURVEY.md 9.1) with nn.Linear/nn.Embedding-style
+    initial distributions -- for timing the oracle without touching any product code."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def emb(name, n):
+        sd[name] = torch.randn(n, dim, generator=g)
+
+    def lin(name, out_f, in_f, bias=True):
+        bound = 1.0 / math.sqrt(in_f)
+        sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound
+        if bias:
+            sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * bound
+
+    def ln(name):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(dim), torch.zeros(dim)
+
+    emb("encoder.embedding.weight", vocab_size)
+    emb("encoder.ast_change_embedding.weight", ast_vocab_size)
+    emb("encoder.mark_embedding.weight", 4)
+    emb("decoder.embedding.weight", vocab_size)
+    for i in range(N_LAYERS):
+        c = f"encoder.combination_list2.{i}"
+        for j in range(3):
+            lin(f"{c}.linear_layers.{j}", dim, dim)
+        lin(f"{c}.output_linear", dim, dim); ln(f"{c}.layernorm")
+        gname = f"encoder.gcn_list.{i}"
+        lin(f"{gname}.fc1", dim, dim); lin(f"{gname}.fc2", dim, dim); ln(f"{gname}.layernorm")
+        for blk in ("attention_list", "cross_attention_list"):
+            a = f"decoder.{blk}.{i}"
+            for nm in ("fc_q", "fc_k", "fc_v", "fc_o"):
+                lin(f"{a}.{nm}", dim, dim)
+            ln(f"{a}.layernorm")
+        f = f"decoder.feed_forward_list.{i}"
+        lin(f"{f}.fc1", 4 * dim, dim); lin(f"{f}.fc2", dim, 4 * dim); ln(f"{f}.layernorm")
+    lin("out_fc", vocab_size, dim)
+    lin("copy_net.LinearSource", dim, dim, bias=False)
+    lin("copy_net.LinearTarget", dim, dim, bias=False)
+    lin("copy_net.LinearRes", 1, dim)
+    lin("copy_net.LinearProb", 2, dim)
+    return sd
+
+
 def train_step(sd_params, optimizer, batch):
     """One reference training step (run_model.py:101-109): loss = sum/sum, backward, Adam."""
     loss_sum, n_tok = forward(sd_params, *batch, stage="train", training=True)

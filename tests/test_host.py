@@ -1,0 +1,123 @@
+"""CPU-side checks: C-ABI library loads and exports every declared symbol, module surface /
+state_dict layout, packed-edge collation, synthetic generator, loud failure without a GPU."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fira_testlib import ROOT, golden_batch, load_batch_golden, load_model_golden, reference_args, seeded_model
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    import __graft_entry__ as g
+    g.build()
+    from fira_icse_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 25
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(handle, name), f"{name} declared in include/fira_b200.h but not exported"
+    lib = _lib.lib()
+    assert lib.fira_version() == 1 and lib.fira_built_arch() == 100
+    out = os.popen(f"nm -D --defined-only {_lib.LIB_PATH}").read()
+    exported = {l.split()[-1] for l in out.splitlines() if " T fira_" in l}
+    assert exported == set(protos), exported ^ set(protos)     # nothing exported that the header hides
+
+
+def test_sass_is_sm100():
+    from fira_icse_b200 import _lib
+    out = os.popen(f"/usr/local/cuda/bin/cuobjdump -lelf {_lib.LIB_PATH} 2>/dev/null").read()
+    assert "sm_100a" in out, out
+
+
+def test_state_dict_layout_and_seeded_init_match_the_reference():
+    gold = load_model_golden()
+    sd = seeded_model().state_dict()
+    assert len(sd) == 338
+    assert list(sd.keys()) == [str(k) for k in gold["param_keys"]]
+    assert [sd[k].numel() for k in sd] == list(gold["param_numel"])
+    s = np.array([sd[k].double().sum().item() for k in sd])
+    a = np.array([sd[k].double().abs().sum().item() for k in sd])
+    assert np.array_equal(s, gold["param_sum"]) and np.array_equal(a, gold["param_abs"])   # bit-identical init
+
+
+def test_dead_parameters_are_the_74_gradless_tensors():
+    m = seeded_model()
+    gold = load_model_golden()
+    live = {id(p) for p in m.live_parameters()}
+    names = sorted(k for k, p in m.named_parameters() if id(p) in live)
+    assert names == sorted(str(k) for k in gold["grad_keys"])
+    assert len(m.dead_parameters()) == 74
+
+
+def test_position_encoding_equals_oracle_table():
+    import fira_oracle as O
+    from fira_icse_b200 import position_encoding
+    for n in (30, 210):
+        assert torch.allclose(position_encoding(n, 256), O.position_table(n, 256), atol=1e-7, rtol=0)
+
+
+def test_no_cpu_fallback():
+    from fira_icse_b200 import FiraLibraryError
+    m = seeded_model()
+    b = golden_batch(0, 2)
+    with pytest.raises((FiraLibraryError, RuntimeError)):
+        m(*b, "train")
+    with pytest.raises((FiraLibraryError, RuntimeError)):
+        m.out_fc(torch.zeros(2, 256))
+
+
+def test_pack_host_reproduces_reference_dense_adjacency():
+    from fira_icse_b200 import PackedEdges
+    coo = golden_batch(0, 5, dense_edge=False)[5]
+    dense = golden_batch(0, 5)[5]
+    rowptr, col, val = PackedEdges.pack_host(coo, 650)
+    pe = PackedEdges(rowptr, col, val, 5, 650, True)
+    assert torch.equal(pe.to_dense(torch.float32), dense.float())
+    assert rowptr.dtype == torch.int32 and col.dtype == torch.int32 and val.dtype == torch.float32
+    # Dataset.py adjacency is symmetric: to 1 ulp in float64, exactly after the model's .float() cast
+    assert torch.equal(dense.float(), dense.float().transpose(1, 2))
+    # duplicates are summed like scipy's toarray()
+    r, c, v = coo[0]
+    rp2, c2, v2 = PackedEdges.pack_host([(np.concatenate((r, r[:3])), np.concatenate((c, c[:3])),
+                                          np.concatenate((v, v[:3])))], 650)
+    d2 = PackedEdges(rp2, c2, v2, 1, 650, True).to_dense()
+    exp = dense[:1].clone()
+    for k in range(3):
+        exp[0, r[k], c[k]] += v[k]
+    assert torch.allclose(d2, exp.float().double(), atol=1e-7)
+
+
+def test_synthetic_generator_follows_the_dataset_distribution():
+    from fira_icse_b200.synth import N_NODES, synth_batch, synth_stress_graphs
+    ids, coo = synth_batch(0, 256)
+    n_code = (ids["sou"] != 0).sum(1)
+    n_sub = (ids["sub_token"] != 0).sum(1)
+    n_ast = (ids["ast_change"] != 0).sum(1)
+    n_tok = (ids["tar_label"][:, 1:] != 0).sum(1)
+    offdiag = np.array([len(r) - N_NODES for r, _, _ in coo])
+    assert 85 < n_code.mean() < 115 and n_code.max() <= 200
+    assert 20 < n_sub.mean() < 34 and n_sub.max() <= 102
+    assert 24 < n_ast.mean() < 40 and n_ast.max() <= 157
+    assert 6 < n_tok.mean() < 10
+    assert 330 < offdiag.mean() < 470, offdiag.mean()          # DataSet: mean 401 directed off-diagonal entries
+    ids2, _ = synth_batch(0, 4)
+    assert all(np.array_equal(ids[k][:4], ids2[k]) for k in ids)   # seeded per commit index
+    r, c, v = coo[0]
+    a = np.zeros((N_NODES, N_NODES)); a[r, c] = v
+    assert np.allclose(a, a.T) and np.allclose(np.diag(a)[400:], 1.0)
+    lab = ids["tar_label"]
+    assert lab.max() < 24650 + 370 and ((lab >= 24650).sum() > 0)
+    g = synth_stress_graphs(0, 1, n_nodes=256, edges_per_relation=512)
+    assert g[0][0].max() < 256
+
+
+def test_shard_range_covers_everything_once():
+    from fira_icse_b200.parallel import shard_range
+    for n in (0, 1, 7, 7661):
+        for w in (1, 2, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
