@@ -256,6 +256,125 @@ __global__ void __launch_bounds__(256) csr_spmm_rows_kernel(const int* __restric
   }
 }
 
+// Version 3: bulk-async (TMA engine, SASS UBLKCP) staging of the neighbour rows in shared memory.
+// Little's law on B200 asks for ~45 KB of reads in flight per SM; v1/v2 hold the gathered rows in
+// registers and spend most of a row's life on the two dependent metadata round trips, so they sit at
+// ~13 KB/SM.  Here a warp takes a group of GR consecutive destination rows, builds their edge list
+// once (one rowptr round trip, one col/val round trip), then every lane fires ONE
+// cp.async.bulk of a whole 1 KB / 512 B neighbour row into the warp's shared-memory stage -- up to EB
+// rows in flight per warp at zero register cost -- and after a single mbarrier wait the warp reduces
+// the staged rows in CSR order (segmented reduction, no atomics).  `addend` rides along as a
+// pseudo-edge of weight 1.
+constexpr int GR = 8;    // destination rows per warp group
+constexpr int EB = 16;   // staged neighbour rows per batch
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) csr_spmm_bulk_kernel(const int* __restrict__ rowptr,
+                                                                   const int* __restrict__ col,
+                                                                   const float* __restrict__ val,
+                                                                   const T* __restrict__ x,
+                                                                   const T* __restrict__ addend, T* __restrict__ y,
+                                                                   Segs s, int N) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[WARPS];
+  constexpr uint32_t ROW_BYTES = D * sizeof(T);
+  const long R = (long)s.B * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * EB * D;
+  const uint32_t bar = smem_u32(&bars[warp]);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  const long group0 = (long)blockIdx.x * WARPS + warp;
+  const long ngroups = (long)gridDim.x * WARPS;
+  const int extra = addend ? 1 : 0;
+  for (long r0 = group0 * GR; r0 < R; r0 += ngroups * GR) {
+    // ---- metadata: one round trip for rowptr, prefix over the group's rows
+    int my_e0 = 0, my_n = 0, my_b = 0;
+    if (lane < GR && r0 + lane < R) {
+      int b, i; seg_unrow(s, r0 + lane, b, i);
+      const long g = (long)b * N + i;
+      my_e0 = rowptr[g]; my_n = rowptr[g + 1] - my_e0 + extra; my_b = b;
+    }
+    int incl = my_n;                                        // inclusive prefix over lanes 0..GR-1
+#pragma unroll
+    for (int o = 1; o < GR; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, GR - 1);
+    const int my_start = incl - my_n;
+    int cur = -1;                                           // destination slot being accumulated
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int kb = 0; kb < total; kb += EB) {
+      const int cnt = min(EB, total - kb);
+      // ---- this lane's edge of the batch: slot, source row pointer, weight (one col/val round trip)
+      int slot = 0; float w = 0.f; const T* src = nullptr;
+      const int id = kb + lane;
+#pragma unroll
+      for (int q = 0; q < GR; ++q) {
+        const int st = __shfl_sync(0xffffffffu, my_start, q), nn = __shfl_sync(0xffffffffu, my_n, q);
+        const int ee = __shfl_sync(0xffffffffu, my_e0, q), bq = __shfl_sync(0xffffffffu, my_b, q);
+        if (lane < cnt && id >= st && id < st + nn) {
+          slot = q;
+          const int j = id - st;
+          if (extra && j == nn - 1) { src = addend + (r0 + q) * D; w = 1.f; }
+          else { src = x + seg_row(s, bq, col[ee + j]) * D; w = val[ee + j]; }
+        }
+      }
+      // ---- fire the bulk copies: lane 0 arms the barrier with the byte count, every lane copies its row
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage reads (generic) before async refill
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * ROW_BYTES);
+      __syncwarp();
+      if (lane < cnt) bulk_g2s(smem_u32(stage + (size_t)lane * D), src, ROW_BYTES, bar);
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
+      parity ^= 1;
+      // ---- segmented reduction of the staged rows, CSR order
+      for (int k = 0; k < cnt; ++k) {
+        const int sk = __shfl_sync(0xffffffffu, slot, k);
+        const float wk = __shfl_sync(0xffffffffu, w, k);
+        if (sk != cur) {
+          if (cur >= 0) Act<T>::store8(y + (r0 + cur) * D + lane * 8, acc);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+          for (int z = cur + 1; z < sk; ++z) Act<T>::store8(y + (r0 + z) * D + lane * 8, acc);   // edge-less rows
+          cur = sk;
+        }
+        float v[8];
+        Act<T>::load8(stage + (size_t)k * D + lane * 8, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(wk, v[q], acc[q]);
+      }
+      __syncwarp();                                         // all lanes done reading before the stage is refilled
+    }
+    if (cur >= 0) Act<T>::store8(y + (r0 + cur) * D + lane * 8, acc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int z = cur + 1; z < GR && r0 + z < R; ++z) Act<T>::store8(y + (r0 + z) * D + lane * 8, acc);
+  }
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, ...)                                                            \
@@ -316,13 +435,29 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
   Segs s{B, n_code, n_sub, n_ast};
   const int N = n_code + n_sub + n_ast;
   const long R = (long)B * N;
-  static const int variant = [] { const char* e = getenv("FIRA_SPMM_VARIANT"); return e ? atoi(e) : 2; }();
+  static const int variant = [] { const char* e = getenv("FIRA_SPMM_VARIANT"); return e ? atoi(e) : 1; }();
   if (variant == 1) {                      // round-1 baseline kernel, kept for A/B profiling
     long ctas = (R + 7) / 8;
     const long cap = 148L * 8 * 4;
     int grid = (int)(ctas < cap ? ctas : cap);
     DISPATCH_T(dtype, csr_spmm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, (const T*)x,
                                                                                    (const T*)addend, (T*)y, s, N);)
+  } else if (variant == 3) {
+    constexpr int WARPS = 6;
+    const size_t smem = (size_t)WARPS * EB * D * (dtype == FIRA_F32 ? 4 : 2);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(csr_spmm_bulk_kernel<float, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           WARPS * EB * D * 4);
+      cudaFuncSetAttribute(csr_spmm_bulk_kernel<__nv_bfloat16, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           WARPS * EB * D * 2);
+      attr_done = true;
+    }
+    long ctas = (R + (long)GR * WARPS - 1) / ((long)GR * WARPS);
+    const long cap = 148L * 8;
+    int grid = (int)(ctas < cap ? ctas : cap);
+    DISPATCH_T(dtype, csr_spmm_bulk_kernel<T, WARPS><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(
+        rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else {
     long ctas = (R + 8 * RPW - 1) / (8 * RPW);
     const long cap = 148L * 16;            // multiple of the SM count; grid-stride beyond

@@ -40,6 +40,12 @@ def run(name, coo, N, segs, dtype_code=0):
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     avg = sum(ms) / len(ms)
+    # size-matched plain copy (same rotation): what a pure stream of these bytes achieves on this box
+    for i in range(iters):
+        ev[i][0].record(st); ys[i % n_pairs].copy_(xs[i % n_pairs]); ev[i][1].record(st)
+    torch.cuda.synchronize()
+    copy_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    copy_avg = sum(copy_ms) / len(copy_ms)
     alg = 2 * R * 256 * esz + (R + 1) * 4 + pe.nnz * 8
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -47,7 +53,9 @@ def run(name, coo, N, segs, dtype_code=0):
                       "dtype": "f32" if dtype_code == 0 else "bf16", "rows": R, "nnz": pe.nnz,
                       "avg_us": round(avg * 1e3, 2), "min_us": round(ms[0] * 1e3, 2),
                       "alg_MB": round(alg / 1e6, 2), "GBps": round(alg / avg / 1e6, 1),
-                      "frac_of_measured_peak": round(alg / avg / 1e6 / peak, 3)}), flush=True)
+                      "frac_of_measured_peak": round(alg / avg / 1e6 / peak, 3),
+                      "same_size_copy_us": round(copy_avg * 1e3, 2),
+                      "same_size_copy_GBps": round(2 * R * 256 * esz / copy_avg / 1e6, 1)}), flush=True)
 
 
 if __name__ == "__main__":
