@@ -3,7 +3,10 @@
 
 Runs only in the build container.  The reference imports nltk for BLEU reporting; nltk is not
 installed, so `nltk.translate.bleu_score` is stubbed (BLEU is printed, never used for ranking).
-Weights: the reference TransModel under torch.manual_seed(0) (no trained checkpoint is shipped);
+Weights: the reference TransModel under torch.manual_seed(0) (no trained checkpoint is shipped) with
+the output projections scaled x20 (SHARPEN) so that the distributions are peaked like a trained
+model's -- with raw random weights every step has p ~ 1e-4, the fp32 probability PRODUCTS of
+run_model.py:271 underflow to 0 after ~12 steps and the ranking degenerates into sort tie-breaking;
 inputs: the first N_COMMITS commits of tests/golden/batch_first128.npz, test batch 8, beam 3.
 Writes tests/golden/beam_first16.npz (chosen sequence per commit, -1 padded).
 """
@@ -18,7 +21,7 @@ import torch
 
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
-N_COMMITS, BATCH = 16, 8
+N_COMMITS, BATCH, SHARPEN = 16, 8, 20.0
 
 
 def main():
@@ -61,6 +64,8 @@ def main():
                        t("sub_token")])
     torch.manual_seed(0)
     model = R.TransModel(R.args)
+    with torch.no_grad():
+        model.out_fc.weight *= SHARPEN; model.out_fc.bias *= SHARPEN; model.copy_net.LinearRes.weight *= SHARPEN
     calls = []
     orig = R.convert_ids_to_tokens
 
@@ -74,7 +79,7 @@ def main():
     out = np.full((N_COMMITS, 30), -1, np.int64)
     for i, h in enumerate(hyps):
         out[i, :len(h)] = h
-    np.savez_compressed(os.path.join(HERE, "beam_first16.npz"), beam_ids=out, batch=BATCH, beam=3)
+    np.savez_compressed(os.path.join(HERE, "beam_first16.npz"), beam_ids=out, batch=BATCH, beam=3, sharpen=SHARPEN)
     print(out[:4])
 
 

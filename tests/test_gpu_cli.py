@@ -29,6 +29,9 @@ def test_beam_search_ids_match_reference_test_loop():
     raw = load_raw_golden()
     vocab = raw["word_vocab"]
     model = copy.deepcopy(seeded_model()).to(DEV).eval()
+    with torch.no_grad():                      # same sharpening as tests/golden/make_golden_beam.py
+        k = float(gold["sharpen"])
+        model.out_fc.weight *= k; model.out_fc.bias *= k; model.copy_net.LinearRes.weight *= k
     bs = int(gold["batch"])
     for lo in range(0, gold["beam_ids"].shape[0], bs):
         b = golden_batch(lo, lo + bs)
