@@ -1,0 +1,319 @@
+// bf16 tensor-core GEMM for the throughput path: tcgen05.mma (UMMA, SASS UTCHMMA) with the fp32
+// accumulator in TMEM, operands staged in shared memory by TMA (cp.async.bulk.tensor, SASS UTMALDG)
+// through a 4-stage mbarrier ring, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> bias / rank-1 / relu ->
+// global).  One 128 x BN output tile per CTA, cta_group::1.
+//
+//   C[M,N] = A (M x K) * B (K x N) + bias[n] + rs[m]*rc[n]      (optional relu; fp32 or bf16 output)
+//
+// Operand storage (bf16, row-major, leading dimension a multiple of 8 elements):
+//   a_kmajor = 1 : A[m*lda + k]   (activations as they are)        a_kmajor = 0 : A[k*lda + m]  (dY^T, X^T)
+//   b_kmajor = 1 : B[n*ldb + k]   (nn.Linear weight [out,in])      b_kmajor = 0 : B[k*ldb + n]
+// The MN-major forms let the weight-gradient GEMM dW = dY^T X read dY and X in place (no transpose
+// pass): TMA fetches [64 k-rows x 64 mn] boxes and the UMMA descriptor carries the MN-major
+// canonical SWIZZLE_128B layout (instruction-descriptor bits 15/16).
+// splits > 1: split-K across blockIdx.z, fp32 partials atomically added into a zero-filled C.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "common.cuh"
+#include "fira_b200.h"
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192; // 6 warps
+
+struct TcParams {
+  void* C; long ldc; int c_is_bf16;
+  int M, N, K;
+  const float* bias; const float* rs; const float* rc;
+  int relu;
+  int splits; int kblocks_per_split;
+  int a_kmajor, b_kmajor;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();      // never hang the GPU on a protocol bug
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, SM100): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Stage layout in shared memory (1024-B aligned, SWIZZLE_128B):
+//   K-major operand  : [rows][64 k]          rows x 128 B, 8-row groups 1024 B apart (SBO = 1024)
+//   MN-major operand : [mn/64][64 k][64 mn]  each 64-mn panel is 64 k-rows x 128 B = 8 KB (LBO = 8192 between
+//                      panels, SBO = 1024 between 8-k groups); one TMA box per panel.
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kblocks_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kblocks_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_addr(&full_bar[s]), 1); mbar_init(smem_addr(&empty_bar[s]), 1); }
+    mbar_init(smem_addr(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_slot)), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(smem_addr(&empty_bar[s]), ph ^ 1);
+      const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+      const uint32_t fb = smem_addr(&full_bar[s]);
+      mbar_expect_tx(fb, STAGE_BYTES);
+      const int k0 = (kb_begin + i) * BK;
+      if (p.a_kmajor) {
+        tma_load_2d(sa, &tmA, k0, m0, fb);                        // box {64 k, 128 m}
+      } else {
+        tma_load_2d(sa, &tmA, m0, k0, fb);                        // two boxes {64 m, 64 k}
+        tma_load_2d(sa + 8192, &tmA, m0 + 64, k0, fb);
+      }
+      if (p.b_kmajor) {
+        tma_load_2d(sb, &tmB, k0, n0, fb);                        // box {64 k, BN n}
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n0 + j * 64, k0, fb);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+    // a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.a_kmajor ? 0u : 1u) << 15) |
+                           ((p.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(smem_addr(&full_bar[s]), ph);
+      tc_fence_after();
+      const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) {
+        // K-major: step 16 k = 32 B inside the 128-B swizzle row; MN-major: step 16 k-rows = 2048 B
+        const uint64_t da = p.a_kmajor ? make_desc(sa + k * 32, 16, 1024) : make_desc(sa + k * 2048, 8192, 1024);
+        const uint64_t db = p.b_kmajor ? make_desc(sb + k * 32, 16, 1024) : make_desc(sb + k * 2048, 8192, 1024);
+        umma_bf16(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(smem_addr(&empty_bar[s]));        // frees the stage when these MMAs have read it
+    }
+    umma_commit(smem_addr(&tmem_full_bar));         // accumulator complete
+  } else if (warp >= 2) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;                   // TMEM lanes [32*quarter, +32) are this warp's
+    const int m = m0 + quarter * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(smem_addr(&tmem_full_bar), 0);
+      tc_fence_after();
+    }
+    const bool first = blockIdx.z == 0;
+    const float rsm = (p.rs && first && m < p.M) ? p.rs[m] : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (m < p.M) {
+        const int nb = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          const int n = nb + j;
+          if (first && n < p.N) {
+            if (p.bias) x += p.bias[n];
+            if (p.rs) x = fmaf(rsm, p.rc[n], x);
+          }
+          if (p.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (p.splits > 1) {
+          float* cp = (float*)p.C + (long)m * p.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nb + j < p.N) atomicAdd(cp + j, v[j]);
+        } else if (p.c_is_bf16) {
+          __nv_bfloat16* cp = (__nv_bfloat16*)p.C + (long)m * p.ldc + nb;
+          if (nb + 31 < p.N && ((p.ldc & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) Act<__nv_bfloat16>::store8(cp + j, v + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* cp = (float*)p.C + (long)m * p.ldc + nb;
+          if (nb + 31 < p.N && ((p.ldc & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(BN));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return (PFN_cuTensorMapEncodeTiled)f;
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix (cols contiguous), box {box_cols, box_rows}, SW128
+int make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, int box_cols, int box_rows) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled unavailable"); return FIRA_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fira_set_error(FIRA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld ld=%ld", (int)r, rows, cols, ld);
+    return FIRA_ERR_CUDA;
+  }
+  return FIRA_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
+    attr = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  return FIRA_OK;
+}
+
+}  // namespace
+
+extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
+                                 long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
+                                 const float* rc, int relu, int splits, void* stream) {
+  FIRA_CHECK_ARG(A && B && C, FIRA_ERR_ARG, "gemm_bf16_tc: null operand");
+  FIRA_CHECK_ARG(M > 0 && N > 0 && K > 0, FIRA_ERR_SHAPE, "gemm_bf16_tc: M=%d N=%d K=%d", M, N, K);
+  FIRA_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, FIRA_ERR_ALIGN, "gemm_bf16_tc: lda/ldb must be multiples of 8");
+  FIRA_CHECK_ARG(fira_aligned16(A) && fira_aligned16(B) && fira_aligned16(C), FIRA_ERR_ALIGN, "gemm_bf16_tc: 16-B alignment");
+  FIRA_CHECK_ARG((rs == nullptr) == (rc == nullptr), FIRA_ERR_ARG, "gemm_bf16_tc: rs/rc must come together");
+  FIRA_CHECK_ARG(!(splits > 1 && (c_is_bf16 || relu)), FIRA_ERR_ARG, "gemm_bf16_tc: split-K needs fp32 C and no relu");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap ta, tb;
+  int rc_;
+  // A: K-major -> matrix [M rows, K cols], box {64 k, 128 m};  MN-major -> matrix [K rows, M cols], box {64 m, 64 k}
+  if (a_kmajor) rc_ = make_map(&ta, A, M, K, lda, BK, BM); else rc_ = make_map(&ta, A, K, M, lda, 64, BK);
+  if (rc_) return rc_;
+  if (b_kmajor) rc_ = make_map(&tb, B, N, K, ldb, BK, BN); else rc_ = make_map(&tb, B, K, N, ldb, 64, BK);
+  if (rc_) return rc_;
+  const int kb_total = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  int per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;
+  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, splits, per, a_kmajor, b_kmajor};
+  if (splits > 1) {
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
+    if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_bf16_tc memset: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
+  }
+  if (BN == 256) rc_ = launch<256>(ta, tb, p, st);
+  else if (BN == 128) rc_ = launch<128>(ta, tb, p, st);
+  else rc_ = launch<64>(ta, tb, p, st);
+  if (rc_) return rc_;
+  FIRA_CHECK_LAUNCH("fira_gemm_bf16_tc");
+  return FIRA_OK;
+}

@@ -544,3 +544,12 @@ class CopyScoresFn(torch.autograd.Function):
         d_Wt = linear_dw(d_tgt, D, dec2, D, Mt, D, D)
         d_dec = linear_dx(d_tgt, D, Wt, Mt).view(B, T, D)
         return d_mem, d_dec, d_Ws, d_Wt, d_wres, d_bres
+
+
+# ============================================================================= bf16 tensor-core GEMM
+def gemm_tc(A, lda, a_kmajor, Bm, ldb, b_kmajor, C, ldc, M, N, K, bias=None, rs=None, rc=None, relu=False,
+            splits=1):
+    """C[M,N] = A(MxK) B(KxN) (+bias, +rs*rc, relu) on tcgen05; A/B bf16, C fp32 or bf16 (by C.dtype)."""
+    call("fira_gemm_bf16_tc", _ptr(A), lda, int(a_kmajor), _ptr(Bm), ldb, int(b_kmajor), _ptr(C), ldc,
+         int(C.dtype == torch.bfloat16), M, N, K, _ptr(bias), _ptr(rs), _ptr(rc), int(relu), splits, _stream())
+    return C

@@ -48,6 +48,14 @@ int fira_gemm_f32(const float* A, long lda, int a_kcontig, const float* B, long 
                   long ldc, int M, int N, int K, const float* bias, const float* rs, const float* rc, int relu,
                   int accumulate, int splits, void* stream);
 
+/* ---- bf16 tensor-core Linear (throughput mode): tcgen05.mma with TMEM accumulators, TMA-staged
+ *      operands.  Same contraction as fira_gemm_f32 on bf16 operands (fp32 accumulate):
+ *      A(m,k) = a_kmajor ? A[m*lda+k] : A[k*lda+m];  B(k,n) = b_kmajor ? B[n*ldb+k] : B[k*ldb+n];
+ *      lda/ldb multiples of 8; C fp32 or bf16 (c_is_bf16); splits>1 = split-K with fp32 atomics. */
+int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
+                      long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
+                      const float* rc, int relu, int splits, void* stream);
+
 /* ---- embeddings -------------------------------------------------------------------------------
  * Encoder node features in segment-major order (all code rows, all sub-token rows, all AST/edit
  * rows): emb[sou]+PE | emb[sub_token] | ast_emb[ast_change]     (gnn_transformer.py:46-52,58).
