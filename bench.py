@@ -282,6 +282,7 @@ def run_gpu_arm(args):
     torch.manual_seed(0)
     model = F.TransModel(model_args()).to(dev)
     model.train()
+    model.set_precision(args.precision)
     dp = DataParallelStep(model, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True))
 
     # every rank gets its own shard of the synthetic stream (graphs shard by commit, no data collective)
@@ -380,11 +381,14 @@ def run_gpu_arm(args):
 
     line = {"metric": "train_commits_per_sec", "value": value, "unit": "commits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
             "config": {"workload": "run_model.py train, 1xB200 per-GPU batch 64 (BASELINE.json configs[1]), "
                                    "synthetic commits with the DataSet node/edge distribution",
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "precision_mode": "fp32 parity (fp32 storage, fp32 FFMA accumulate)",
+                       "precision_mode": ("bf16 throughput (bf16 activations, tcgen05 GEMMs with fp32 TMEM accumulators, "
+                                          "fp32 parameters/statistics/gradients)" if args.precision == "bf16" else
+                                          "fp32 parity (fp32 storage, fp32 FFMA accumulate)"),
                        "optimizer": "Adam lr 1e-4 (torch fused), dropout on (0.1 / GCN 0.2)",
                        "l2": f"{N_POOL} distinct batches rotated; one step touches >1 GB of activations (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "commits/s", "h2d_bytes_per_step": int(h2d_bytes(pool_host[0])),
@@ -404,6 +408,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("FIRA_PRECISION", "bf16"), choices=["bf16", "fp32"],
+                    help="bf16 = BASELINE.json config (default); fp32 = parity mode")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling runs only (ncu): leave out the host-CPU leg")
     args = ap.parse_args()

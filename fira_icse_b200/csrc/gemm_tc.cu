@@ -30,7 +30,7 @@ struct TcParams {
   void* C; long ldc; int c_is_bf16;
   int M, N, K;
   const float* bias; const float* rs; const float* rc;
-  int relu;
+  int relu; int accumulate;
   int splits; int kblocks_per_split;
   int a_kmajor, b_kmajor;
 };
@@ -211,19 +211,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __nv_bfloat16* cp = (__nv_bfloat16*)p.C + (long)m * p.ldc + nb;
           if (nb + 31 < p.N && ((p.ldc & 7) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) Act<__nv_bfloat16>::store8(cp + j, v + j);
+            for (int j = 0; j < 32; j += 8) {
+              if (p.accumulate) {
+                float old[8];
+                Act<__nv_bfloat16>::load8(cp + j, old);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[j + q] += old[q];
+              }
+              Act<__nv_bfloat16>::store8(cp + j, v + j);
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) cp[j] = __float2bfloat16_rn(p.accumulate ? v[j] + __bfloat162float(cp[j]) : v[j]);
           }
         } else {
           float* cp = (float*)p.C + (long)m * p.ldc + nb;
           if (nb + 31 < p.N && ((p.ldc & 3) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.accumulate) {
+                const float4 c4 = *reinterpret_cast<const float4*>(cp + j);
+                o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
+              }
+              *reinterpret_cast<float4*>(cp + j) = o;
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = v[j];
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
           }
         }
       }
@@ -284,7 +300,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cuda
 
 extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
                                  long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
-                                 const float* rc, int relu, int splits, void* stream) {
+                                 const float* rc, int relu, int accumulate, int splits, void* stream) {
   FIRA_CHECK_ARG(A && B && C, FIRA_ERR_ARG, "gemm_bf16_tc: null operand");
   FIRA_CHECK_ARG(M > 0 && N > 0 && K > 0, FIRA_ERR_SHAPE, "gemm_bf16_tc: M=%d N=%d K=%d", M, N, K);
   FIRA_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, FIRA_ERR_ALIGN, "gemm_bf16_tc: lda/ldb must be multiples of 8");
@@ -305,8 +321,8 @@ extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const vo
   if (splits > kb_total) splits = kb_total;
   int per = (kb_total + splits - 1) / splits;
   splits = (kb_total + per - 1) / per;
-  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, splits, per, a_kmajor, b_kmajor};
-  if (splits > 1) {
+  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits, per, a_kmajor, b_kmajor};
+  if (splits > 1 && !accumulate) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
     if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_bf16_tc memset: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   }

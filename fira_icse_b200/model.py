@@ -9,6 +9,8 @@ fira_icse_b200.graph.PackedEdges (what the packed loader emits).  Sub-modules `e
 `decoder`, `out_fc`, `copy_net` are individually callable, as the reference's beam loop
 requires (run_model.py:204,256,257,259).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -60,6 +62,15 @@ class TransModel(nn.Module):
         self.out_fc = _OutFc(args.embedding_dim, args.vocab_size)
         self.gate_fc = nn.Linear(args.embedding_dim, 1)   # dead upstream too (Model.py:35)
         self.copy_net = CopyNet(args)
+        self.set_precision(os.environ.get("FIRA_PRECISION", "fp32"))
+
+    def set_precision(self, precision):
+        """'fp32' (parity mode, default) or 'bf16' (throughput mode: bf16 activations, tcgen05 GEMMs)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.encoder.bf16 = self.decoder.bf16 = precision == "bf16"
+        return self
 
     def dead_parameters(self):
         return self.encoder.dead_parameters() + list(self.gate_fc.parameters())
@@ -83,7 +94,8 @@ class TransModel(nn.Module):
         dec = self.decoder(tar, memory, mem_mask, tar != 0)
         label = self.shifted_label(tar_label)
         want_ids = stage != "train"
-        loss_sum, _, ids = ops.HeadFn.apply(want_ids, memory, dec, _u8(mem_mask), _i32(label).view(-1),
+        loss_sum, _, ids = ops.HeadFn.apply(want_ids, self.precision == "bf16", memory, dec, _u8(mem_mask),
+                                            _i32(label).view(-1),
                                             self.out_fc.weight, self.out_fc.bias, *self.copy_net.flat_params())
         if stage == "train":
             return loss_sum, (label != 0).sum()

@@ -124,9 +124,8 @@ class FeedForward(_KernelBacked):
 
 
 def _run_cfg(module, stream_base=0):
-    training = module.training and torch.is_grad_enabled()
     return {"training": module.training, "seed": ops.make_seed() if module.training else 0,
-            "stream_base": stream_base, "heads": module.num_head, "grad": training}
+            "stream_base": stream_base, "heads": module.num_head, "bf16": bool(getattr(module, "bf16", False))}
 
 
 class Encoder(nn.Module):

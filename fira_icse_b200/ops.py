@@ -2,19 +2,25 @@
 head) whose forward/backward are explicit sequences of libfira_b200 launches on the current
 stream.  No torch compute op sits on the path (torch supplies memory, streams, autograd glue).
 
+Precision modes (cfg["bf16"]):
+  * fp32 parity mode  : fp32 activations, every Linear on fira_gemm_f32 (fp32 FFMA) -- logits within
+                        1e-4 of the reference.
+  * bf16 throughput   : bf16 activations, every large Linear on fira_gemm_bf16_tc (tcgen05.mma, TMEM
+                        fp32 accumulators, TMA operands); statistics, parameters, parameter gradients
+                        and the handful of tiny products (4 x 256 value table, 256^3 weight merges,
+                        2-wide gate) stay fp32.
+
 Buffer conventions
   * node buffer: segment-major rows  [B*210 code | B*160 sub-token | B*280 AST/edit] x 256
     (kills the per-layer torch.cat/slice of gnn_transformer.py:58,86); `Xc` holds the code rows a
     Combination reads, `Gin` holds every row a GCN layer reads.
-  * all activations of one precision mode share one storage dtype (fp32 parity / bf16 throughput).
 """
 import torch
 
 from . import _lib
-from ._lib import FIRA_F32, call
+from ._lib import FIRA_BF16, FIRA_F32, call
 
 D = 256
-_TORCH_DT = {FIRA_F32: torch.float32, _lib.FIRA_BF16: torch.bfloat16}
 
 
 def _stream():
@@ -35,16 +41,11 @@ def _require_cuda(*ts):
                 "(the CPU reference lives in oracle/ and is test infrastructure only)")
 
 
-def new(shape, like, dtype=None, zero=False):
-    f = torch.zeros if zero else torch.empty
-    return f(shape, dtype=dtype or like.dtype, device=like.device)
-
-
-# ----------------------------------------------------------------------------- GEMM helpers (fp32)
 def _ceil(a, b):
     return (a + b - 1) // b
 
 
+# ----------------------------------------------------------------------------- fp32 GEMM (parity mode)
 def _pick_splits(M, N, K, relu):
     if relu:
         return 1
@@ -64,56 +65,137 @@ def gemm_raw(A, lda, a_k, Bp, ldb, b_k, C, ldc, M, N, K, bias=None, rs=None, rc=
 
 
 def linear(x, W, b=None, relu=False, out=None, ld_out=None, rs=None, rc=None, M=None, x_off=0, ldx=None):
-    """y[M,N] = x[M,K] W[N,K]^T + b (+ rs[m]*rc[n]).  Returns `out` ([M, ld_out] buffer)."""
+    """fp32: y[M,N] = x[M,K] W[N,K]^T + b (+ rs[m]*rc[n]).  Returns `out` ([M, ld_out] buffer)."""
     N, K = W.shape
     M = x.shape[0] if M is None else M
     ldx = K if ldx is None else ldx
     ld_out = N if ld_out is None else ld_out
     if out is None:
-        out = new((M, ld_out), x)
+        out = torch.empty((M, ld_out), dtype=torch.float32, device=x.device)
     gemm_raw(_ptr(x, x_off), ldx, 1, _ptr(W), K, 1, _ptr(out), ld_out, M, N, K, bias=b, rs=rs, rc=rc, relu=relu)
     return out
 
 
 def linear_dx(dy, ld_dy, W, M, out=None, accumulate=False, dy_off=0, n=None):
-    """dx[M,K] (+)= dy[M,N] W[N,K]."""
+    """fp32: dx[M,K] (+)= dy[M,N] W[N,K]."""
     N, K = W.shape
     n = N if n is None else n
     if out is None:
-        out = new((M, K), dy)
+        out = torch.empty((M, K), dtype=torch.float32, device=dy.device)
     gemm_raw(_ptr(dy, dy_off), ld_dy, 1, _ptr(W), K, 0, _ptr(out), K, M, K, n, accumulate=accumulate)
     return out
 
 
 def linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0):
-    """dW[N,K] = dy[M,N]^T x[M,K]."""
-    dW = new((N, K), dy, dtype=torch.float32)
+    """fp32: dW[N,K] = dy[M,N]^T x[M,K]."""
+    dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
     gemm_raw(_ptr(dy, dy_off), ld_dy, 0, _ptr(x, x_off), ldx, 0, _ptr(dW), K, N, K, M)
     return dW
 
 
-def colsum(x, ld, M, N, weight=None, x_off=0, dtype=FIRA_F32):
+# ----------------------------------------------------------------------------- bf16 tcgen05 GEMM
+def gemm_tc(A, lda, a_kmajor, Bm, ldb, b_kmajor, C, ldc, M, N, K, bias=None, rs=None, rc=None, relu=False,
+            accumulate=False, splits=1, a_off=0, b_off=0, c_off=0):
+    """C[M,N] = A(MxK) B(KxN) (+bias, +rs*rc, relu) on tcgen05; A/B bf16, C fp32 or bf16 (by C.dtype)."""
+    call("fira_gemm_bf16_tc", _ptr(A, a_off), lda, int(a_kmajor), _ptr(Bm, b_off), ldb, int(b_kmajor), _ptr(C, c_off),
+         ldc, int(C.dtype == torch.bfloat16), M, N, K, _ptr(bias), _ptr(rs), _ptr(rc), int(relu), int(accumulate),
+         splits, _stream())
+    return C
+
+
+def _tc_splits(tiles, kblocks):
+    """split-K factor that brings a small-output GEMM to ~2 CTAs per SM"""
+    if tiles >= 148:
+        return 1
+    return max(1, min(kblocks // 4 if kblocks >= 8 else 1, _ceil(296, tiles)))
+
+
+def colsum(x, ld, M, N, weight=None, x_off=0, dtype=None):
+    if dtype is None:
+        dtype = FIRA_BF16 if x.dtype == torch.bfloat16 else FIRA_F32
     out = torch.zeros(N, dtype=torch.float32, device=x.device)
     call("fira_colsum", _ptr(x, x_off), ld, M, N, _ptr(weight), _ptr(out), dtype, _stream())
     return out
 
 
-def ln_fwd(z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid, dtype=FIRA_F32):
-    stats = torch.empty((2, rows), dtype=torch.float32, device=z.device)
-    call("fira_ln_residual_fwd", _ptr(z), _ptr(resid), _ptr(gamma), _ptr(beta), _ptr(outA), _ptr(outB), split,
-         _ptr(stats), _ptr(stats, rows), rows, D, float(p), seed, sid, dtype, _stream())
-    return stats
+class Prec:
+    """Precision context of one forward/backward pair: dtype codes, buffers, Linear dispatch."""
+
+    def __init__(self, bf16, wcache=None):
+        self.bf16 = bool(bf16)
+        self.code = FIRA_BF16 if self.bf16 else FIRA_F32
+        self.tdt = torch.bfloat16 if self.bf16 else torch.float32
+        self.wcache = {} if wcache is None else wcache
+
+    def empty(self, shape, dev):
+        return torch.empty(shape, dtype=self.tdt, device=dev)
+
+    def w(self, W):
+        """GEMM-operand form of a parameter: itself (fp32 mode) or a bf16 copy cached for fwd+bwd."""
+        if not self.bf16:
+            return W
+        k = (W.data_ptr(), tuple(W.shape))
+        if k not in self.wcache:
+            self.wcache[k] = (W, W.detach().to(torch.bfloat16))     # keep W alive: the key is its address
+        return self.wcache[k][1]
+
+    # y = x W^T + b
+    def linear(self, x, W, b=None, relu=False, out=None, ld_out=None, rs=None, rc=None, M=None, ldx=None, x_off=0):
+        if not self.bf16:
+            return linear(x, W, b, relu=relu, out=out, ld_out=ld_out, rs=rs, rc=rc, M=M, ldx=ldx, x_off=x_off)
+        N, K = W.shape
+        M = x.shape[0] if M is None else M
+        ldx = K if ldx is None else ldx
+        ld_out = N if ld_out is None else ld_out
+        if out is None:
+            out = torch.empty((M, ld_out), dtype=torch.bfloat16, device=x.device)
+        return gemm_tc(x, ldx, 1, self.w(W), K, 1, out, ld_out, M, N, K, bias=b, rs=rs, rc=rc, relu=relu, a_off=x_off)
+
+    # dx (+)= dy W
+    def linear_dx(self, dy, ld_dy, W, M, out=None, accumulate=False, dy_off=0):
+        if not self.bf16:
+            return linear_dx(dy, ld_dy, W, M, out=out, accumulate=accumulate, dy_off=dy_off)
+        N, K = W.shape
+        if out is None:
+            out = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
+        return gemm_tc(dy, ld_dy, 1, self.w(W), K, 0, out, K, M, K, N, accumulate=accumulate, a_off=dy_off)
+
+    # dW = dy^T x   (fp32 result in both modes)
+    def linear_dw(self, dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0):
+        if not self.bf16:
+            return linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=dy_off, x_off=x_off)
+        dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        bn = 256 if K > 128 else (128 if K > 64 else 64)
+        splits = _tc_splits(_ceil(N, 128) * _ceil(K, bn), _ceil(M, 64))
+        return gemm_tc(dy, ld_dy, 0, x, ldx, 0, dW, K, N, K, M, splits=splits, a_off=dy_off, b_off=x_off)
+
+    def ln_fwd(self, z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid):
+        stats = torch.empty((2, rows), dtype=torch.float32, device=z.device)
+        call("fira_ln_residual_fwd", _ptr(z), _ptr(resid), _ptr(gamma), _ptr(beta), _ptr(outA), _ptr(outB), split,
+             _ptr(stats), _ptr(stats, rows), rows, D, float(p), seed, sid, self.code, _stream())
+        return stats
+
+    def ln_bwd(self, dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=None, accum=False):
+        dz = torch.empty_like(z)
+        if d_resid is None:
+            d_resid = torch.empty_like(z)
+        dgb = torch.zeros((2, D), dtype=torch.float32, device=z.device)
+        call("fira_ln_residual_bwd", _ptr(dA), _ptr(dB), split, _ptr(z), _ptr(resid), _ptr(stats), _ptr(stats, rows),
+             _ptr(gamma), _ptr(dz), _ptr(d_resid), int(accum), _ptr(dgb), _ptr(dgb, D), rows, D, float(p), seed, sid,
+             self.code, _stream())
+        return dz, d_resid, dgb[0], dgb[1]
 
 
-def ln_bwd(dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=None, accum=False, dtype=FIRA_F32):
-    dz = torch.empty_like(z)
-    if d_resid is None:
-        d_resid = torch.empty_like(z)
-    dgb = torch.zeros((2, D), dtype=torch.float32, device=z.device)
-    call("fira_ln_residual_bwd", _ptr(dA), _ptr(dB), split, _ptr(z), _ptr(resid), _ptr(stats), _ptr(stats, rows),
-         _ptr(gamma), _ptr(dz), _ptr(d_resid), int(accum), _ptr(dgb), _ptr(dgb, D), rows, D, float(p), seed, sid,
-         dtype, _stream())
-    return dz, d_resid, dgb[0], dgb[1]
+# fp32-mode free functions kept for the kernel unit tests
+_F32 = Prec(False)
+
+
+def ln_fwd(z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid):
+    return _F32.ln_fwd(z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid)
+
+
+def ln_bwd(dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=None, accum=False):
+    return _F32.ln_bwd(dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=d_resid, accum=accum)
 
 
 def make_seed():
@@ -147,13 +229,15 @@ class EncoderFn(torch.autograd.Function):
         p_comb = cfg["p_comb"] if training else 0.0
         p_gcn = cfg["p_gcn"] if training else 0.0
         heads = cfg["heads"]
-        f32 = dict(dtype=torch.float32, device=emb.device)
+        pr = Prec(cfg.get("bf16", False))
+        dev = emb.device
+        f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
 
-        Xc = torch.empty((Mc, D), **f32)
-        Gin = torch.empty((R, D), **f32)
+        Xc = pr.empty((Mc, D), dev)
+        Gin = pr.empty((R, D), dev)
         call("fira_embed_nodes_fwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(emb), _ptr(ast_emb),
-             _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, FIRA_F32, st)
+             _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
         rs = edges.rowsum(n_code, n_sub, n_ast)
         saved = []
         for i in range(L):
@@ -162,31 +246,32 @@ class EncoderFn(torch.autograd.Function):
             # ---- Combination (gnn_transformer.py:192-205, combination_layer.py:7-17)
             Wqk = torch.cat((Wq, Wk), 0)
             bqk = torch.cat((bq, bk), 0)
-            QK = linear(Xc, Wqk, bqk)                                  # [Mc, 512] = [q | k]
-            Vtab = linear(mark_emb, Wv, bv)                            # [4, 256]: value has 4 distinct rows
-            Cd = torch.empty((Mc, D), **f32)
+            QK = pr.linear(Xc, Wqk, bqk)                               # [Mc, 512] = [q | k]
+            Vtab = linear(mark_emb, Wv, bv)                            # fp32 [4, 256]: value has 4 distinct rows
+            Cd = pr.empty((Mc, D), dev)
             call("fira_comb_gate_fwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(Cd), Mc, D, D // heads,
-                 float(p_comb), seed, sid + 0, FIRA_F32, st)
-            Zc = linear(Cd, Wo, bo)
-            st_c = ln_fwd(Zc, Xc, clw, clb, Gin, Gin, Mc, Mc, p_comb, seed, sid + 1)   # -> Gin[:Mc]
+                 float(p_comb), seed, sid + 0, pr.code, st)
+            Zc = pr.linear(Cd, Wo, bo)
+            st_c = pr.ln_fwd(Zc, Xc, clw, clb, Gin, Gin, Mc, Mc, p_comb, seed, sid + 1)   # -> Gin[:Mc]
             # ---- GCN (gnn_transformer.py:74-86)
-            G = torch.empty((R, D), **f32)
+            G = pr.empty((R, D), dev)
             call("fira_gcn_aggregate", _ptr(edges.rowptr), _ptr(edges.col), _ptr(edges.val), _ptr(Gin), None,
-                 _ptr(G), B, n_code, n_sub, n_ast, D, FIRA_F32, st)
+                 _ptr(G), B, n_code, n_sub, n_ast, D, pr.code, st)
             Wc = torch.empty((D, D), **f32)                            # W2 @ W1
             gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=1)
             c1 = torch.empty((D,), **f32)                              # W2 @ b1
             gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
-            Z = linear(G, Wc, b2, rs=rs, rc=c1)
-            Xc_n = torch.empty((Mc, D), **f32)
-            Gin_n = torch.empty((R, D), **f32)
-            st_g = ln_fwd(Z, Gin, glw, glb, Xc_n, Gin_n, Mc, R, p_gcn, seed, sid + 2)
+            Z = pr.linear(G, Wc, b2, rs=rs, rc=c1)
+            Xc_n = pr.empty((Mc, D), dev)
+            Gin_n = pr.empty((R, D), dev)
+            st_g = pr.ln_fwd(Z, Gin, glw, glb, Xc_n, Gin_n, Mc, R, p_gcn, seed, sid + 2)
             saved.append((Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1))
             Xc, Gin = Xc_n, Gin_n
-        memory = torch.empty((B, n_code + n_sub, D), **f32)
-        call("fira_pack_memory", _ptr(Xc), _ptr(Gin), _ptr(memory), B, n_code, n_sub, D, FIRA_F32, st)
+        memory = pr.empty((B, n_code + n_sub, D), dev)
+        call("fira_pack_memory", _ptr(Xc), _ptr(Gin), _ptr(memory), B, n_code, n_sub, D, pr.code, st)
 
         ctx.saved = saved
+        ctx.wcache = pr.wcache
         ctx.misc = (cfg, sou, mark, ast_change, sub_token, edges, rs, B, n_code, n_sub, n_ast, p_comb, p_gcn)
         ctx.save_for_backward(emb, ast_emb, mark_emb, *lp)
         return memory
@@ -199,13 +284,15 @@ class EncoderFn(torch.autograd.Function):
         R, Mc = B * N, B * n_code
         L = len(lp) // ENC_LAYER_PARAMS
         seed, heads = cfg["seed"], cfg["heads"]
-        f32 = dict(dtype=torch.float32, device=emb.device)
+        pr = Prec(cfg.get("bf16", False), ctx.wcache)
+        dev = emb.device
+        f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
         et = edges.t()
-        d_mem = d_mem.contiguous()
-        dXc = torch.empty((Mc, D), **f32)
-        dGin = torch.empty((R, D), **f32)
-        call("fira_unpack_memory", _ptr(d_mem), _ptr(dXc), _ptr(dGin), B, n_code, n_sub, n_ast, D, FIRA_F32, st)
+        d_mem = d_mem.contiguous().to(pr.tdt)
+        dXc = pr.empty((Mc, D), dev)
+        dGin = pr.empty((R, D), dev)
+        call("fira_unpack_memory", _ptr(d_mem), _ptr(dXc), _ptr(dGin), B, n_code, n_sub, n_ast, D, pr.code, st)
         d_mark_emb = torch.zeros_like(mark_emb)
         grads = [None] * len(lp)
         for i in reversed(range(L)):
@@ -213,14 +300,14 @@ class EncoderFn(torch.autograd.Function):
             Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1 = ctx.saved[i]
             sid = cfg["stream_base"] + i * 8
             # ---- GCN backward
-            dZ, dRes, d_glw, d_glb = ln_bwd(dXc, dGin, Mc, Z, Gin, st_g, glw, R, p_gcn, seed, sid + 2)
+            dZ, dRes, d_glw, d_glb = pr.ln_bwd(dXc, dGin, Mc, Z, Gin, st_g, glw, R, p_gcn, seed, sid + 2)
             d_b2 = colsum(dZ, D, R, D)
             d_c1 = colsum(dZ, D, R, D, weight=rs)
-            dWc = linear_dw(dZ, D, G, D, R, D, D)
-            dG = linear_dx(dZ, D, Wc, R)
-            dGin_i = torch.empty((R, D), **f32)
+            dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
+            dG = pr.linear_dx(dZ, D, Wc, R)
+            dGin_i = pr.empty((R, D), dev)
             call("fira_gcn_aggregate", _ptr(et.rowptr), _ptr(et.col), _ptr(et.val), _ptr(dG), _ptr(dRes),
-                 _ptr(dGin_i), B, n_code, n_sub, n_ast, D, FIRA_F32, st)
+                 _ptr(dGin_i), B, n_code, n_sub, n_ast, D, pr.code, st)
             d_W2 = torch.empty((D, D), **f32)       # dWc W1^T + d_c1 b1^T
             gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=1)
             d_W1 = torch.empty((D, D), **f32)       # W2^T dWc
@@ -228,19 +315,19 @@ class EncoderFn(torch.autograd.Function):
             d_b1 = torch.empty((D,), **f32)         # W2^T d_c1
             gemm_raw(_ptr(W2), D, 0, _ptr(d_c1), 1, 0, _ptr(d_b1), 1, D, 1, D, splits=1)
             # ---- Combination backward (rows < Mc of dGin_i are d(comb output))
-            dXc_n = torch.empty((Mc, D), **f32)
-            dZc, _, d_clw, d_clb = ln_bwd(dGin_i, dGin_i, Mc, Zc, Xc, st_c, clw, Mc, p_comb, seed, sid + 1,
-                                          d_resid=dXc_n)
+            dXc_n = pr.empty((Mc, D), dev)
+            dZc, _, d_clw, d_clb = pr.ln_bwd(dGin_i, dGin_i, Mc, Zc, Xc, st_c, clw, Mc, p_comb, seed, sid + 1,
+                                             d_resid=dXc_n)
             d_bo = colsum(dZc, D, Mc, D)
-            d_Wo = linear_dw(dZc, D, Cd, D, Mc, D, D)
-            dCd = linear_dx(dZc, D, Wo, Mc)
-            dQK = torch.empty((Mc, 2 * D), **f32)
+            d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D)
+            dCd = pr.linear_dx(dZc, D, Wo, Mc)
+            dQK = pr.empty((Mc, 2 * D), dev)
             dVtab = torch.zeros((4, D), **f32)
             call("fira_comb_gate_bwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(dCd), _ptr(dQK), _ptr(dVtab),
-                 Mc, D, D // heads, float(p_comb), seed, sid + 0, FIRA_F32, st)
+                 Mc, D, D // heads, float(p_comb), seed, sid + 0, pr.code, st)
             d_bqk = colsum(dQK, 2 * D, Mc, 2 * D)
-            d_Wqk = linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D)
-            linear_dx(dQK, 2 * D, Wqk, Mc, out=dXc_n, accumulate=True)
+            d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D)
+            pr.linear_dx(dQK, 2 * D, Wqk, Mc, out=dXc_n, accumulate=True)
             d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D)
             d_bv = colsum(dVtab, D, 4, D)
             linear_dx(dVtab, D, Wv, 4, out=d_mark_emb, accumulate=True)
@@ -251,7 +338,7 @@ class EncoderFn(torch.autograd.Function):
         d_emb = torch.zeros_like(emb)
         d_ast = torch.zeros_like(ast_emb)
         call("fira_embed_nodes_bwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(dXc), _ptr(dGin),
-             _ptr(d_emb), _ptr(d_ast), B, n_code, n_sub, n_ast, D, FIRA_F32, st)
+             _ptr(d_emb), _ptr(d_ast), B, n_code, n_sub, n_ast, D, pr.code, st)
         d_mark_emb[0].zero_()     # padding_idx=0 (gnn_transformer.py:39)
         return (None, None, None, None, None, None, None, d_emb, d_ast, d_mark_emb, *grads)
 
@@ -274,16 +361,19 @@ class DecoderFn(torch.autograd.Function):
         H = cfg["heads"]
         training, seed = cfg["training"], cfg["seed"]
         p = cfg["p_dec"] if training else 0.0
-        f32 = dict(dtype=torch.float32, device=dec_emb.device)
+        pr = Prec(cfg.get("bf16", False))
+        dev = dec_emb.device
+        f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
-        memory = memory.contiguous()
+        mem_dtype = memory.dtype
+        memory = memory.contiguous().to(pr.tdt)
 
-        X = torch.empty((Mt, D), **f32)
-        call("fira_embed_rows_fwd", _ptr(tar), _ptr(dec_emb), _ptr(pos_table), _ptr(X), Mt, T, D, FIRA_F32, st)
+        X = pr.empty((Mt, D), dev)
+        call("fira_embed_rows_fwd", _ptr(tar), _ptr(dec_emb), _ptr(pos_table), _ptr(X), Mt, T, D, pr.code, st)
         Wkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])], 0)     # [L*512, 256]
         bkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])], 0)
         ldkv = L * 2 * D
-        KV = linear(memory.view(Ms, D), Wkv, bkv)                                                 # [Ms, L*512]
+        KV = pr.linear(memory.view(Ms, D), Wkv, bkv)                                              # [Ms, L*512]
         saved = []
         for i in range(L):
             (sWq, sbq, sWk, sbk, sWv, sbv, sWo, sbo, slw, slb,
@@ -293,47 +383,49 @@ class DecoderFn(torch.autograd.Function):
             # ---- masked self-attention (gnn_transformer.py:117-119)
             Wqkv = torch.cat((sWq, sWk, sWv), 0)
             bqkv = torch.cat((sbq, sbk, sbv), 0)
-            QKV = linear(X, Wqkv, bqkv)                                  # [Mt, 768]
-            ctx1 = torch.empty((Mt, D), **f32)
+            QKV = pr.linear(X, Wqkv, bqkv)                               # [Mt, 768]
+            ctx1 = pr.empty((Mt, D), dev)
             st1 = torch.empty((B, H, T, 2), **f32)
             call("fira_attn_fwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
-                 _ptr(ctx1), D, _ptr(st1), B, H, T, T, D // H, FIRA_F32, st)
-            Z1 = linear(ctx1, sWo, sbo)
-            X1 = torch.empty((Mt, D), **f32)
-            ls1 = ln_fwd(Z1, X, slw, slb, X1, X1, Mt, Mt, p, seed, sid + 0)
+                 _ptr(ctx1), D, _ptr(st1), B, H, T, T, D // H, pr.code, st)
+            Z1 = pr.linear(ctx1, sWo, sbo)
+            X1 = pr.empty((Mt, D), dev)
+            ls1 = pr.ln_fwd(Z1, X, slw, slb, X1, X1, Mt, Mt, p, seed, sid + 0)
             # ---- cross-attention over the encoder memory (gnn_transformer.py:120)
-            Q = linear(X1, cWq, cbq)
-            ctx2 = torch.empty((Mt, D), **f32)
+            Q = pr.linear(X1, cWq, cbq)
+            ctx2 = pr.empty((Mt, D), dev)
             st2 = torch.empty((B, H, T, 2), **f32)
             call("fira_attn_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
-                 _ptr(mem_mask), 0, _ptr(ctx2), D, _ptr(st2), B, H, T, S, D // H, FIRA_F32, st)
-            Z2 = linear(ctx2, cWo, cbo)
-            X2 = torch.empty((Mt, D), **f32)
-            ls2 = ln_fwd(Z2, X1, clw, clb, X2, X2, Mt, Mt, p, seed, sid + 1)
+                 _ptr(mem_mask), 0, _ptr(ctx2), D, _ptr(st2), B, H, T, S, D // H, pr.code, st)
+            Z2 = pr.linear(ctx2, cWo, cbo)
+            X2 = pr.empty((Mt, D), dev)
+            ls2 = pr.ln_fwd(Z2, X1, clw, clb, X2, X2, Mt, Mt, p, seed, sid + 1)
             # ---- feed-forward (gnn_transformer.py:170-174)
-            Hh = linear(X2, fW1, fb1, relu=True)                          # [Mt, 1024]
-            Z3 = linear(Hh, fW2, fb2)
-            X3 = torch.empty((Mt, D), **f32)
-            ls3 = ln_fwd(Z3, X2, flw, flb, X3, X3, Mt, Mt, p, seed, sid + 2)
+            Hh = pr.linear(X2, fW1, fb1, relu=True)                       # [Mt, 1024]
+            Z3 = pr.linear(Hh, fW2, fb2)
+            X3 = pr.empty((Mt, D), dev)
+            ls3 = pr.ln_fwd(Z3, X2, flw, flb, X3, X3, Mt, Mt, p, seed, sid + 2)
             saved.append((X, Wqkv, QKV, ctx1, st1, Z1, ls1, X1, Q, ctx2, st2, Z2, ls2, X2, Hh, Z3, ls3))
             X = X3
         ctx.saved = saved
-        ctx.misc = (cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p)
+        ctx.wcache = pr.wcache
+        ctx.misc = (cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p, mem_dtype)
         ctx.save_for_backward(dec_emb, *lp)
         return X.view(B, T, D)
 
     @staticmethod
     def backward(ctx, d_out):
-        cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p = ctx.misc
+        cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p, mem_dtype = ctx.misc
         dec_emb, *lp = ctx.saved_tensors
         Mt, Ms = B * T, B * S
         L = len(lp) // DEC_LAYER_PARAMS
         H, seed = cfg["heads"], cfg["seed"]
-        f32 = dict(dtype=torch.float32, device=dec_emb.device)
+        pr = Prec(cfg.get("bf16", False), ctx.wcache)
+        dev = dec_emb.device
         st = _stream()
         ldkv = L * 2 * D
-        dX = d_out.contiguous().view(Mt, D)
-        dKV = torch.empty((Ms, ldkv), **f32)
+        dX = d_out.contiguous().to(pr.tdt).view(Mt, D)
+        dKV = pr.empty((Ms, ldkv), dev)
         grads = [None] * len(lp)
         F = 4 * D
         for i in reversed(range(L)):
@@ -343,38 +435,38 @@ class DecoderFn(torch.autograd.Function):
             X, Wqkv, QKV, ctx1, st1, Z1, ls1, X1, Q, ctx2, st2, Z2, ls2, X2, Hh, Z3, ls3 = ctx.saved[i]
             sid = cfg["stream_base"] + 64 + i * 8
             # ---- FFN
-            dZ3, dX2, d_flw, d_flb = ln_bwd(dX, dX, Mt, Z3, X2, ls3, flw, Mt, p, seed, sid + 2)
+            dZ3, dX2, d_flw, d_flb = pr.ln_bwd(dX, dX, Mt, Z3, X2, ls3, flw, Mt, p, seed, sid + 2)
             d_fb2 = colsum(dZ3, D, Mt, D)
-            d_fW2 = linear_dw(dZ3, D, Hh, F, Mt, D, F)
-            dHh = linear_dx(dZ3, D, fW2, Mt)                              # [Mt, 1024]
-            call("fira_relu_bwd", _ptr(Hh), _ptr(dHh), Mt * F, FIRA_F32, st)
+            d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F)
+            dHh = pr.linear_dx(dZ3, D, fW2, Mt)                           # [Mt, 1024]
+            call("fira_relu_bwd", _ptr(Hh), _ptr(dHh), Mt * F, pr.code, st)
             d_fb1 = colsum(dHh, F, Mt, F)
-            d_fW1 = linear_dw(dHh, F, X2, D, Mt, F, D)
-            linear_dx(dHh, F, fW1, Mt, out=dX2, accumulate=True)
+            d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D)
+            pr.linear_dx(dHh, F, fW1, Mt, out=dX2, accumulate=True)
             # ---- cross-attention
-            dZ2, dX1, d_clw, d_clb = ln_bwd(dX2, dX2, Mt, Z2, X1, ls2, clw, Mt, p, seed, sid + 1)
+            dZ2, dX1, d_clw, d_clb = pr.ln_bwd(dX2, dX2, Mt, Z2, X1, ls2, clw, Mt, p, seed, sid + 1)
             d_cbo = colsum(dZ2, D, Mt, D)
-            d_cWo = linear_dw(dZ2, D, ctx2, D, Mt, D, D)
-            dctx2 = linear_dx(dZ2, D, cWo, Mt)
-            dQ = torch.empty((Mt, D), **f32)
+            d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D)
+            dctx2 = pr.linear_dx(dZ2, D, cWo, Mt)
+            dQ = pr.empty((Mt, D), dev)
             call("fira_attn_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
                  _ptr(mem_mask), 0, _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
-                 _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, FIRA_F32, st)
+                 _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
             d_cbq = colsum(dQ, D, Mt, D)
-            d_cWq = linear_dw(dQ, D, X1, D, Mt, D, D)
-            linear_dx(dQ, D, cWq, Mt, out=dX1, accumulate=True)
+            d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D)
+            pr.linear_dx(dQ, D, cWq, Mt, out=dX1, accumulate=True)
             # ---- self-attention
-            dZ1, dX0, d_slw, d_slb = ln_bwd(dX1, dX1, Mt, Z1, X, ls1, slw, Mt, p, seed, sid + 0)
+            dZ1, dX0, d_slw, d_slb = pr.ln_bwd(dX1, dX1, Mt, Z1, X, ls1, slw, Mt, p, seed, sid + 0)
             d_sbo = colsum(dZ1, D, Mt, D)
-            d_sWo = linear_dw(dZ1, D, ctx1, D, Mt, D, D)
-            dctx1 = linear_dx(dZ1, D, sWo, Mt)
-            dQKV = torch.empty((Mt, 3 * D), **f32)
+            d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D)
+            dctx1 = pr.linear_dx(dZ1, D, sWo, Mt)
+            dQKV = pr.empty((Mt, 3 * D), dev)
             call("fira_attn_bwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
                  _ptr(dctx1), D, _ptr(st1), _ptr(dQKV), 3 * D, _ptr(dQKV, D), 3 * D, _ptr(dQKV, 2 * D), 3 * D,
-                 B, H, T, T, D // H, FIRA_F32, st)
+                 B, H, T, T, D // H, pr.code, st)
             d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D)
-            d_Wqkv = linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D)
-            linear_dx(dQKV, 3 * D, Wqkv, Mt, out=dX0, accumulate=True)
+            d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D)
+            pr.linear_dx(dQKV, 3 * D, Wqkv, Mt, out=dX0, accumulate=True)
             grads[i * 26:(i + 1) * 26] = [
                 d_Wqkv[:D], d_bqkv[:D], d_Wqkv[D:2 * D], d_bqkv[D:2 * D], d_Wqkv[2 * D:], d_bqkv[2 * D:],
                 d_sWo, d_sbo, d_slw, d_slb,
@@ -385,14 +477,14 @@ class DecoderFn(torch.autograd.Function):
         # hoisted K/V projections of the memory: one weight-grad GEMM, one input-grad GEMM
         mem2 = memory.view(Ms, D)
         d_bkv = colsum(dKV, ldkv, Ms, ldkv)
-        d_Wkv = linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D)
-        d_mem = linear_dx(dKV, ldkv, Wkv, Ms).view(B, S, D)
+        d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D)
+        d_mem = pr.linear_dx(dKV, ldkv, Wkv, Ms).view(B, S, D).to(mem_dtype)
         for i in range(L):
             o = i * 2 * D
             grads[i * 26 + 12], grads[i * 26 + 13] = d_Wkv[o:o + D], d_bkv[o:o + D]
             grads[i * 26 + 14], grads[i * 26 + 15] = d_Wkv[o + D:o + 2 * D], d_bkv[o + D:o + 2 * D]
         d_emb = torch.zeros_like(dec_emb)
-        call("fira_embed_rows_bwd", _ptr(tar), _ptr(dX), _ptr(d_emb), Mt, D, FIRA_F32, st)
+        call("fira_embed_rows_bwd", _ptr(tar), _ptr(dX), _ptr(d_emb), Mt, D, pr.code, st)
         return (None, None, d_mem, None, None, None, d_emb, *grads)
 
 
@@ -401,41 +493,46 @@ def _ld_logits(V):
     return (V + 63) // 64 * 64
 
 
-def copy_scores_fwd(memory2, dec2, Ws, Wt, wres, bres, B, T, S):
-    src = linear(memory2, Ws)                     # [B*S, 256]
-    tgt = linear(dec2, Wt)                        # [B*T, 256]
+def copy_scores_fwd(pr, memory2, dec2, Ws, Wt, wres, bres, B, T, S):
+    src = pr.linear(memory2, Ws)                  # [B*S, 256]
+    tgt = pr.linear(dec2, Wt)                     # [B*T, 256]
     sc = torch.empty((B, T, S), dtype=torch.float32, device=dec2.device)
-    call("fira_copy_scores_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(sc), B, T, S, D, FIRA_F32,
+    call("fira_copy_scores_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(sc), B, T, S, D, pr.code,
          _stream())
     return src, tgt, sc
 
 
 class HeadFn(torch.autograd.Function):
     """Model.py:54-86 fused: out_fc, CopyNet, both softmaxes, gate mixing, log(clamp), shifted-label
-    NLL -- returns (loss_sum, argmax ids or None).  The B x 30 x 25,020 distribution is never built."""
+    NLL -- returns (loss_sum, per-position nll, argmax ids or None).  The B x 30 x 25,020 distribution
+    is never built."""
 
     @staticmethod
-    def forward(ctx, want_argmax, memory, dec, mem_mask, label, Wout, bout, Ws, Wt, Wres, bres, Wp, bp):
+    def forward(ctx, want_argmax, bf16, memory, dec, mem_mask, label, Wout, bout, Ws, Wt, Wres, bres, Wp, bp):
         _require_cuda(memory, dec, Wout)
         B, S, _ = memory.shape
         T = dec.shape[1]
         V = Wout.shape[0]
         Mt, Ms = B * T, B * S
-        f32 = dict(dtype=torch.float32, device=dec.device)
+        pr = Prec(bf16)
+        dev = dec.device
+        f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
-        memory2 = memory.contiguous().view(Ms, D)
-        dec2 = dec.contiguous().view(Mt, D)
+        memory2 = memory.contiguous().to(pr.tdt).view(Ms, D)
+        dec2 = dec.contiguous().to(pr.tdt).view(Mt, D)
+        dec32 = dec2 if not pr.bf16 else dec2.float()            # the 2-wide gate stays on the fp32 path
         ldl = _ld_logits(V)
-        logits = torch.empty((Mt, ldl), **f32)
-        linear(dec2, Wout, bout, out=logits, ld_out=ldl)
-        src, tgt, sc = copy_scores_fwd(memory2, dec2, Ws, Wt, Wres, bres, B, T, S)
-        gl = linear(dec2, Wp, bp)                 # [Mt, 2]
+        logits = pr.empty((Mt, ldl), dev)
+        pr.linear(dec2, Wout, bout, out=logits, ld_out=ldl)
+        src, tgt, sc = copy_scores_fwd(pr, memory2, dec2, Ws, Wt, Wres, bres, B, T, S)
+        gl = linear(dec32, Wp, bp)                # fp32 [Mt, 2]
         stats = torch.empty((Mt, 8), **f32)
         nll = torch.empty((Mt,), **f32)
-        amax = torch.empty((Mt,), dtype=torch.int32, device=dec.device) if want_argmax else None
+        amax = torch.empty((Mt,), dtype=torch.int32, device=dev) if want_argmax else None
         call("fira_pointer_mix_nll_fwd", _ptr(logits), ldl, _ptr(sc), _ptr(gl), _ptr(mem_mask), _ptr(label),
-             _ptr(stats), _ptr(nll), _ptr(amax), Mt, T, V, S, FIRA_F32, st)
-        ctx.misc = (memory2, dec2, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V)
+             _ptr(stats), _ptr(nll), _ptr(amax), Mt, T, V, S, pr.code, st)
+        ctx.misc = (pr, memory2, dec2, dec32, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V,
+                    memory.dtype, dec.dtype)
         ctx.save_for_backward(Wout, Ws, Wt, Wres, Wp)
         loss_sum = colsum(nll, 1, Mt, 1).view(())
         ids = amax.view(B, T) if want_argmax else None
@@ -445,39 +542,45 @@ class HeadFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_nll, g_ids):
-        memory2, dec2, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V = ctx.misc
+        (pr, memory2, dec2, dec32, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V,
+         mem_dt, dec_dt) = ctx.misc
         Wout, Ws, Wt, Wres, Wp = ctx.saved_tensors
         Mt, Ms = B * T, B * S
-        f32 = dict(dtype=torch.float32, device=dec2.device)
+        dev = dec2.device
+        f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
         up = g_loss.contiguous().float()
-        dlogits = torch.empty((Mt, ldl), **f32)
+        dlogits = pr.empty((Mt, ldl), dev)
         dsc = torch.empty((B, T, S), **f32)
         dgl = torch.empty((Mt, 2), **f32)
-        active = torch.empty((Mt,), dtype=torch.uint8, device=dec2.device)
+        active = torch.empty((Mt,), dtype=torch.uint8, device=dev)
         call("fira_pointer_mix_nll_bwd", _ptr(logits), ldl, _ptr(sc), _ptr(mem_mask), _ptr(label), _ptr(stats),
-             _ptr(up), _ptr(dlogits), _ptr(dsc), _ptr(dgl), _ptr(active), Mt, T, V, S, FIRA_F32, st)
-        # vocabulary projection
-        d_bout = colsum(dlogits, ldl, Mt, V)
-        d_Wout = linear_dw(dlogits, ldl, dec2, D, Mt, V, D)
-        d_dec = linear_dx(dlogits, ldl, Wout, Mt)
-        # gate
-        d_bp = colsum(dgl, 2, Mt, 2)
-        d_Wp = linear_dw(dgl, 2, dec2, D, Mt, 2, D)
-        linear_dx(dgl, 2, Wp, Mt, out=d_dec, accumulate=True)
+             _ptr(up), _ptr(dlogits), _ptr(dsc), _ptr(dgl), _ptr(active), Mt, T, V, S, pr.code, st)
         # pointer scores
-        d_src = torch.empty((Ms, D), **f32)
+        d_src = pr.empty((Ms, D), dev)
         d_tgt = torch.zeros((Mt, D), **f32)
         d_wres = torch.zeros((1, D), **f32)
         d_bres = torch.zeros((1,), **f32)
         call("fira_copy_scores_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(d_src),
-             _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, FIRA_F32, st)
-        d_Ws = linear_dw(d_src, D, memory2, D, Ms, D, D)
-        d_mem = linear_dx(d_src, D, Ws, Ms)
-        d_Wt = linear_dw(d_tgt, D, dec2, D, Mt, D, D)
+             _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
+        d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D)
+        d_mem = pr.linear_dx(d_src, D, Ws, Ms)
+        # vocabulary projection (the big one), gate and target projection; d_dec accumulates in fp32
+        d_bout = colsum(dlogits, ldl, Mt, V)
+        d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D)
+        if pr.bf16:
+            d_dec = torch.empty((Mt, D), **f32)
+            gemm_tc(dlogits, ldl, 1, pr.w(Wout), D, 0, d_dec, D, Mt, D, V,
+                    splits=_tc_splits(_ceil(Mt, 128), _ceil(V, 64)))
+        else:
+            d_dec = linear_dx(dlogits, ldl, Wout, Mt)
+        d_bp = colsum(dgl, 2, Mt, 2)
+        d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D)
+        linear_dx(dgl, 2, Wp, Mt, out=d_dec, accumulate=True)
+        d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D)
         linear_dx(d_tgt, D, Wt, Mt, out=d_dec, accumulate=True)
-        return (None, d_mem.view(B, S, D), d_dec.view(B, T, D), None, None, d_Wout, d_bout, d_Ws, d_Wt, d_wres,
-                d_bres, d_Wp, d_bp)
+        return (None, None, d_mem.view(B, S, D).to(mem_dt), d_dec.view(B, T, D).to(dec_dt), None, None, d_Wout, d_bout,
+                d_Ws, d_Wt, d_wres, d_bres, d_Wp, d_bp)
 
 
 # ============================================================================= module-surface pieces
@@ -488,7 +591,7 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, W, b):
         _require_cuda(x, W)
         N, K = W.shape
-        x2 = x.contiguous().view(-1, K)
+        x2 = x.contiguous().float().view(-1, K)
         M = x2.shape[0]
         ld = (N + 3) // 4 * 4
         out = torch.empty((M, ld), dtype=torch.float32, device=x.device)
@@ -503,7 +606,7 @@ class LinearFn(torch.autograd.Function):
         x2, W = ctx.saved_tensors
         N, K = W.shape
         M = x2.shape[0]
-        dy2 = dy.contiguous().view(M, N)
+        dy2 = dy.contiguous().float().view(M, N)
         dx = linear_dx(dy2, N, W, M).view(ctx.shape)
         dW = linear_dw(dy2, N, x2, K, M, N, K)
         db = colsum(dy2, N, M, N) if ctx.has_bias else None
@@ -511,16 +614,16 @@ class LinearFn(torch.autograd.Function):
 
 
 class CopyScoresFn(torch.autograd.Function):
-    """model.copy_net(memory, tar_em) -> raw pointer scores [B,T,S] (Model.py:15-18)."""
+    """model.copy_net(memory, tar_em) -> raw pointer scores [B,T,S] (Model.py:15-18), fp32 path."""
 
     @staticmethod
     def forward(ctx, memory, dec, Ws, Wt, Wres, bres):
         _require_cuda(memory, dec, Ws)
         B, S, _ = memory.shape
         T = dec.shape[1]
-        memory2 = memory.contiguous().view(B * S, D)
-        dec2 = dec.contiguous().view(B * T, D)
-        src, tgt, sc = copy_scores_fwd(memory2, dec2, Ws, Wt, Wres, bres, B, T, S)
+        memory2 = memory.contiguous().float().view(B * S, D)
+        dec2 = dec.contiguous().float().view(B * T, D)
+        src, tgt, sc = copy_scores_fwd(_F32, memory2, dec2, Ws, Wt, Wres, bres, B, T, S)
         ctx.misc = (memory2, dec2, src, tgt, B, T, S)
         ctx.save_for_backward(Ws, Wt, Wres)
         return sc
@@ -544,12 +647,3 @@ class CopyScoresFn(torch.autograd.Function):
         d_Wt = linear_dw(d_tgt, D, dec2, D, Mt, D, D)
         d_dec = linear_dx(d_tgt, D, Wt, Mt).view(B, T, D)
         return d_mem, d_dec, d_Ws, d_Wt, d_wres, d_bres
-
-
-# ============================================================================= bf16 tensor-core GEMM
-def gemm_tc(A, lda, a_kmajor, Bm, ldb, b_kmajor, C, ldc, M, N, K, bias=None, rs=None, rc=None, relu=False,
-            splits=1):
-    """C[M,N] = A(MxK) B(KxN) (+bias, +rs*rc, relu) on tcgen05; A/B bf16, C fp32 or bf16 (by C.dtype)."""
-    call("fira_gemm_bf16_tc", _ptr(A), lda, int(a_kmajor), _ptr(Bm), ldb, int(b_kmajor), _ptr(C), ldc,
-         int(C.dtype == torch.bfloat16), M, N, K, _ptr(bias), _ptr(rs), _ptr(rc), int(relu), splits, _stream())
-    return C

@@ -51,10 +51,11 @@ int fira_gemm_f32(const float* A, long lda, int a_kcontig, const float* B, long 
 /* ---- bf16 tensor-core Linear (throughput mode): tcgen05.mma with TMEM accumulators, TMA-staged
  *      operands.  Same contraction as fira_gemm_f32 on bf16 operands (fp32 accumulate):
  *      A(m,k) = a_kmajor ? A[m*lda+k] : A[k*lda+m];  B(k,n) = b_kmajor ? B[n*ldb+k] : B[k*ldb+n];
- *      lda/ldb multiples of 8; C fp32 or bf16 (c_is_bf16); splits>1 = split-K with fp32 atomics. */
+ *      lda/ldb multiples of 8; C fp32 or bf16 (c_is_bf16); accumulate: C += result;
+ *      splits>1 = split-K with fp32 atomics (C zero-filled first unless accumulate). */
 int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
                       long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
-                      const float* rc, int relu, int splits, void* stream);
+                      const float* rc, int relu, int accumulate, int splits, void* stream);
 
 /* ---- embeddings -------------------------------------------------------------------------------
  * Encoder node features in segment-major order (all code rows, all sub-token rows, all AST/edit

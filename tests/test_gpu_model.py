@@ -62,7 +62,7 @@ def test_intermediates_match_reference(model, gold):
         dec = model.decoder(tar, memory, mem_mask, tar != 0)
         logits = model.out_fc(dec)
         scores, gate = model.copy_net(memory, dec)
-        _, nll, _ = ops.HeadFn.apply(False, memory, dec, mem_mask.to(torch.uint8),
+        _, nll, _ = ops.HeadFn.apply(False, False, memory, dec, mem_mask.to(torch.uint8),
                                      model.shifted_label(tar_label).to(torch.int32).view(-1),
                                      model.out_fc.weight, model.out_fc.bias, *model.copy_net.flat_params())
     real = mem_mask[:4].unsqueeze(-1).cpu().numpy()
@@ -168,3 +168,61 @@ def test_empty_and_ragged_inputs(model):
     with torch.no_grad():
         loss_sum, n_tok = model(*b, "train")
     assert int(n_tok) == 0 and loss_sum.item() == 0.0
+
+
+# ------------------------------------------------------------------ bf16 throughput mode (tcgen05 GEMMs)
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def test_bf16_mode_tracks_fp32_mode(model, gold):
+    """bf16 activations + tensor-core GEMMs: loss within 2e-2 of the reference, gradients aligned."""
+    import copy
+    m = copy.deepcopy(model).set_precision("bf16")
+    n = int(gold["grad_commits"])
+    batch = to_dev(golden_batch(0, n))
+    m.zero_grad(set_to_none=True)
+    loss_sum, n_tok = m(*batch, "train")
+    loss = loss_sum / n_tok
+    loss.backward()
+    ref = float(gold["grad_loss"])
+    assert abs(loss.item() - ref) <= 2e-2 * ref, (loss.item(), ref)
+    model.zero_grad(set_to_none=True)
+    l32, t32 = model(*batch, "train")
+    (l32 / t32).backward()
+    p32, p16 = dict(model.named_parameters()), dict(m.named_parameters())
+    worst = 1.0
+    for k, p in p32.items():
+        if p.grad is None:
+            assert p16[k].grad is None
+            continue
+        if p.grad.norm().item() < 1e-6:
+            continue
+        c = _cos(p.grad, p16[k].grad)
+        worst = min(worst, c)
+        assert c > 0.98, (k, c)
+        r = p16[k].grad.norm().item() / p.grad.norm().item()
+        assert 0.9 < r < 1.1, (k, r)
+    print("worst bf16-vs-fp32 gradient cosine", worst)
+    with torch.no_grad():
+        ids16 = m(*batch, "dev")
+        ids32 = model(*batch, "dev")
+    assert (ids16 == ids32).float().mean().item() > 0.9
+
+
+def test_bf16_training_reduces_loss(model):
+    import copy
+    m = copy.deepcopy(model).set_precision("bf16")
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    batch = to_dev(golden_batch(32, 48))
+    losses = []
+    for _ in range(6):
+        loss_sum, n_tok = m(*batch, "train")
+        loss = loss_sum / n_tok
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
