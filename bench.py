@@ -276,6 +276,7 @@ def run_gpu_arm(args):
         dist.barrier()
     import fira_icse_b200 as F
     from fira_icse_b200 import _lib
+    from fira_icse_b200.engine import GraphedTrainStep
     from fira_icse_b200.parallel import DataParallelStep
 
     B = PER_GPU_BATCH
@@ -283,11 +284,14 @@ def run_gpu_arm(args):
     model = F.TransModel(model_args()).to(dev)
     model.train()
     model.set_precision(args.precision)
-    dp = DataParallelStep(model, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True))
 
     # every rank gets its own shard of the synthetic stream (graphs shard by commit, no data collective)
     pool_host = [host_batch((rank * N_POOL + i) * B, B, pin=True) for i in range(N_POOL)]
     pool_dev = [device_batch(hb, dev, B) for hb in pool_host]
+
+    def host_list(hb):
+        t, csr, _ = hb
+        return [t["sou"], t["tar"], None, t["mark"], t["ast_change"], csr, t["tar_label"], t["sub_token"]]
     torch.cuda.synchronize()
 
     def barrier():
@@ -308,9 +312,35 @@ def run_gpu_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    last_loss = [0.0]
+    if args.graph:
+        # whole step captured in a CUDA graph (fira_icse_b200/engine.py): one cudaGraphLaunch per step
+        eng = GraphedTrainStep(model, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True))
+        eng.load(pool_dev[0])
+        c0 = _lib.LAUNCH_COUNT
+        eng.capture(warmup=3)
+        launches_per_step = (_lib.LAUNCH_COUNT - c0) // 4            # 3 warm-up iterations + the captured one
+        optimizer, bucket = eng.optimizer, eng.bucket
+
+        def resident_step(i):
+            eng.step(pool_dev[i % N_POOL])
+
+        def e2e_step(i):
+            eng.step(host_list(pool_host[i % N_POOL]))               # pinned host -> static device buffers -> replay
+            last_loss[0] = (eng.loss_sum / eng.n_local).item()       # D2H read of the step's result
+    else:
+        dp = DataParallelStep(model, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True))
+        optimizer, bucket = dp.optimizer, dp.bucket
+        launches_per_step = None
+
+        def resident_step(i):
+            dp.step(pool_dev[i % N_POOL])
+
+        def e2e_step(i):
+            loss, _ = dp.step(device_batch(pool_host[i % N_POOL], dev, B))
+            last_loss[0] = loss.item()
+
     # ---- device-resident arm ("value")
-    def resident_step(i):
-        dp.step(pool_dev[i % N_POOL])
     for i in range(args.warmup):
         resident_step(i)
     sampler = ClockSampler(local)
@@ -318,17 +348,11 @@ def run_gpu_arm(args):
         sampler.start()
     launches0 = _lib.LAUNCH_COUNT
     ms = timed(resident_step, args.steps)
-    launches = _lib.LAUNCH_COUNT - launches0
+    launches = (_lib.LAUNCH_COUNT - launches0) if launches_per_step is None else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end-to-end arm: pinned host batch -> H2D -> TransModel.forward -> backward -> Adam -> loss D2H
-    last_loss = [0.0]
-
-    def e2e_step(i):
-        batch = device_batch(pool_host[i % N_POOL], dev, B)
-        loss, _ = dp.step(batch)
-        last_loss[0] = loss.item()                     # D2H read of the step's result
     for i in range(min(3, args.warmup)):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
@@ -340,19 +364,24 @@ def run_gpu_arm(args):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import fira_oracle as O
         t, _, coo = pool_host[0]
-        dense = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo]).pin_memory()    # test-infra helper only
-                                                                                            # builds the INPUT
+        dense = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo]).pin_memory()    # builds the INPUT only
+
         def dense_step(i):
             d = {k: v.to(dev, non_blocking=True) for k, v in t.items()}
-            loss, _ = dp.step([d["sou"], d["tar"], d["attr"], d["mark"], d["ast_change"],
-                               dense.to(dev, non_blocking=True), d["tar_label"], d["sub_token"]])
+            bucket.zero()
+            loss_sum, n_tok = model(d["sou"], d["tar"], None, d["mark"], d["ast_change"],
+                                    dense.to(dev, non_blocking=True), d["tar_label"], d["sub_token"], "train")
+            loss = loss_sum / n_tok
+            loss.backward()
+            optimizer.step()
             last_loss[0] = loss.item()
         dense_step(0)
         k = min(args.steps, 5)
         ms_d = timed(dense_step, k)
         dense_info = {"value": B * k / (ms_d * 1e-3), "unit": "commits/s",
                       "h2d_bytes_per_step": int(dense.numel() * 8 + sum(v.numel() * 8 for v in t.values())),
-                      "note": "edge passed as the reference's dense float64 [B,650,650] host tensor (Dataset.py:340)"}
+                      "note": "eager (no CUDA graph); edge passed as the reference's dense float64 [B,650,650] host "
+                              "tensor (Dataset.py:340)"}
 
     if rank != 0:
         if world > 1:
@@ -390,6 +419,7 @@ def run_gpu_arm(args):
                                           "fp32 parameters/statistics/gradients)" if args.precision == "bf16" else
                                           "fp32 parity (fp32 storage, fp32 FFMA accumulate)"),
                        "optimizer": "Adam lr 1e-4 (torch fused), dropout on (0.1 / GCN 0.2)",
+                       "launch": "whole step replayed as one CUDA graph" if args.graph else "eager launches",
                        "l2": f"{N_POOL} distinct batches rotated; one step touches >1 GB of activations (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "commits/s", "h2d_bytes_per_step": int(h2d_bytes(pool_host[0])),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
@@ -410,6 +440,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FIRA_PRECISION", "bf16"), choices=["bf16", "fp32"],
                     help="bf16 = BASELINE.json config (default); fp32 = parity mode")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling runs only (ncu): leave out the host-CPU leg")
     args = ap.parse_args()

@@ -26,10 +26,32 @@ struct AttnArgs {
 
 template <typename T>
 __device__ __forceinline__ void load_tile(float* dst, const T* src, long ld, int rows, int tid, int nthr) {
-  // rows x 32 -> dst[row][KPAD]
-  for (int idx = tid; idx < rows * DH; idx += nthr) {
-    int r = idx / DH, d = idx % DH;
-    dst[r * KPAD + d] = Act<T>::ld(src + (long)r * ld + d);
+  // rows x 32 -> dst[row][KPAD].  16-byte loads (a head slice of a row is 128 B fp32 / 64 B bf16), several
+  // independent loads in flight per thread: the scalar version of round 1 was latency-bound (one 4-byte
+  // load per thread per trip, ~40 us per 370-row tile).
+  constexpr int EPV = 16 / sizeof(T);          // elements per 16-byte vector
+  constexpr int VPR = DH / EPV;                // vectors per row
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld * sizeof(T)) % 16 == 0);
+  if (vec_ok) {
+#pragma unroll 4
+    for (int idx = tid; idx < rows * VPR; idx += nthr) {
+      const int r = idx / VPR, c = idx % VPR;
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + (long)r * ld + c * EPV);
+      float* o = dst + r * KPAD + c * EPV;
+      if constexpr (sizeof(T) == 4) {
+        o[0] = __uint_as_float(raw.x); o[1] = __uint_as_float(raw.y);
+        o[2] = __uint_as_float(raw.z); o[3] = __uint_as_float(raw.w);
+      } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); o[2 * q] = f.x; o[2 * q + 1] = f.y; }
+      }
+    }
+  } else {
+    for (int idx = tid; idx < rows * DH; idx += nthr) {
+      int r = idx / DH, d = idx % DH;
+      dst[r * KPAD + d] = Act<T>::ld(src + (long)r * ld + d);
+    }
   }
 }
 

@@ -162,15 +162,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     umma_commit(smem_addr(&tmem_full_bar));         // accumulator complete
   } else if (warp >= 2) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> smem (lane = row) -> global (lane = column) =====
+    // tcgen05.ld hands every lane ONE accumulator row; storing that straight to global makes each warp
+    // store touch 32 different rows (32 sectors per instruction: measured ~30 us per tile, round 1).  So the
+    // warp first parks its 32 x BN fp32 block in the (now idle) pipeline stages with a +16 B row pitch
+    // (conflict-free float4 writes), then streams it out row by row: 32 lanes x 8 consecutive columns =
+    // 512 B (bf16) / 1 KB (fp32) contiguous per store; bias / rank-1 / relu / accumulate / split-K atomics
+    // are applied on the way out with per-lane column constants.
     const int quarter = warp & 3;                   // TMEM lanes [32*quarter, +32) are this warp's
-    const int m = m0 + quarter * 32 + lane;
+    constexpr int PITCH = BN + 4;                   // floats
+    float* stg = reinterpret_cast<float*>(smem_dyn + (base - smem_addr(smem_dyn))) + (size_t)quarter * 32 * PITCH;
     if (nkb > 0) {
       mbar_wait(smem_addr(&tmem_full_bar), 0);
       tc_fence_after();
     }
-    const bool first = blockIdx.z == 0;
-    const float rsm = (p.rs && first && m < p.M) ? p.rs[m] : 0.f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -189,57 +194,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (m < p.M) {
-        const int nb = n0 + c * 32;
-        float v[32];
+      float* dst = stg + (size_t)lane * PITCH + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          const int n = nb + j;
-          if (first && n < p.N) {
-            if (p.bias) x += p.bias[n];
-            if (p.rs) x = fmaf(rsm, p.rc[n], x);
-          }
-          if (p.relu) x = fmaxf(x, 0.f);
-          v[j] = x;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+    __syncwarp();
+    const bool first = blockIdx.z == 0;
+    const int mrow0 = m0 + quarter * 32;
+    const int col = lane * 8;
+    if (col < BN) {
+      const int n = n0 + col;
+      float bv[8], rcv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bv[j] = (p.bias && first && n + j < p.N) ? p.bias[n + j] : 0.f;
+        rcv[j] = (p.rs && first && n + j < p.N) ? p.rc[n + j] : 0.f;
+      }
+      const bool full = n + 7 < p.N;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = mrow0 + rr;
+        if (m >= p.M) break;
+        const float rsm = (p.rs && first) ? p.rs[m] : 0.f;          // same address in every lane: one broadcast load
+        float v[8];
+        const float4 x0 = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + col);
+        const float4 x1 = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + col + 4);
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fmaf(rsm, rcv[j], v[j] + bv[j]);
+          if (p.relu) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.splits > 1) {
-          float* cp = (float*)p.C + (long)m * p.ldc + nb;
+          float* cp = (float*)p.C + (long)m * p.ldc + n;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (nb + j < p.N) atomicAdd(cp + j, v[j]);
+          for (int j = 0; j < 8; ++j) if (n + j < p.N) atomicAdd(cp + j, v[j]);
         } else if (p.c_is_bf16) {
-          __nv_bfloat16* cp = (__nv_bfloat16*)p.C + (long)m * p.ldc + nb;
-          if (nb + 31 < p.N && ((p.ldc & 7) == 0)) {
+          __nv_bfloat16* cp = (__nv_bfloat16*)p.C + (long)m * p.ldc + n;
+          if (full && ((p.ldc & 7) == 0)) {
+            if (p.accumulate) {
+              float old[8];
+              Act<__nv_bfloat16>::load8(cp, old);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (p.accumulate) {
-                float old[8];
-                Act<__nv_bfloat16>::load8(cp + j, old);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[j + q] += old[q];
-              }
-              Act<__nv_bfloat16>::store8(cp + j, v + j);
+              for (int j = 0; j < 8; ++j) v[j] += old[j];
             }
+            Act<__nv_bfloat16>::store8(cp, v);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) cp[j] = __float2bfloat16_rn(p.accumulate ? v[j] + __bfloat162float(cp[j]) : v[j]);
+            for (int j = 0; j < 8; ++j)
+              if (n + j < p.N) cp[j] = __float2bfloat16_rn(p.accumulate ? v[j] + __bfloat162float(cp[j]) : v[j]);
           }
         } else {
-          float* cp = (float*)p.C + (long)m * p.ldc + nb;
-          if (nb + 31 < p.N && ((p.ldc & 3) == 0)) {
+          float* cp = (float*)p.C + (long)m * p.ldc + n;
+          if (full && ((p.ldc & 3) == 0)) {
+            if (p.accumulate) {
+              float old[8];
+              Act<float>::load8(cp, old);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.accumulate) {
-                const float4 c4 = *reinterpret_cast<const float4*>(cp + j);
-                o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
-              }
-              *reinterpret_cast<float4*>(cp + j) = o;
+              for (int j = 0; j < 8; ++j) v[j] += old[j];
             }
+            Act<float>::store8(cp, v);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
           }
         }
       }

@@ -109,7 +109,8 @@ template <typename T>
 __global__ void ln_fwd_kernel(const T* __restrict__ z, const T* __restrict__ resid, const float* __restrict__ gamma,
                               const float* __restrict__ beta, T* __restrict__ outA, T* __restrict__ outB, long split,
                               float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, float p_drop,
-                              uint64_t seed, uint32_t stream_id) {
+                              uint64_t seed, const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  if (seed_ctr) seed += *seed_ctr;
   const int lane = threadIdx.x & 31;
   float g[8], bt[8];
   Act<float>::load8(gamma + lane * 8, g);
@@ -148,7 +149,9 @@ __global__ void ln_bwd_kernel(const T* __restrict__ doutA, const T* __restrict__
                               const T* __restrict__ z, const T* __restrict__ resid, const float* __restrict__ mean_in,
                               const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ d_z,
                               T* __restrict__ d_resid, int d_resid_accum, float* __restrict__ d_gamma,
-                              float* __restrict__ d_beta, long rows, float p_drop, uint64_t seed, uint32_t stream_id) {
+                              float* __restrict__ d_beta, long rows, float p_drop, uint64_t seed,
+                              const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  if (seed_ctr) seed += *seed_ctr;
   __shared__ float red[2][ROWS_PER_CTA][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[8], dg[8], db[8];
@@ -215,7 +218,9 @@ __global__ void ln_bwd_kernel(const T* __restrict__ doutA, const T* __restrict__
 template <typename T>
 __global__ void comb_gate_fwd_kernel(const T* __restrict__ qk, long ld_qk, const float* __restrict__ vtab,
                                      const int* __restrict__ mark, T* __restrict__ out, long rows, float scale,
-                                     float p_drop, uint64_t seed, uint32_t stream_id) {
+                                     float p_drop, uint64_t seed, const uint64_t* __restrict__ seed_ctr,
+                                     uint32_t stream_id) {
+  if (seed_ctr) seed += *seed_ctr;
   const int lane = threadIdx.x & 31;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * ROWS_PER_CTA) {
@@ -240,7 +245,8 @@ template <typename T>
 __global__ void comb_gate_bwd_kernel(const T* __restrict__ qk, long ld_qk, const float* __restrict__ vtab,
                                      const int* __restrict__ mark, const T* __restrict__ d_out, T* __restrict__ d_qk,
                                      float* __restrict__ d_vtab, long rows, float scale, float p_drop, uint64_t seed,
-                                     uint32_t stream_id) {
+                                     const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  if (seed_ctr) seed += *seed_ctr;
   __shared__ float red[ROWS_PER_CTA][4][D + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dv[4][8];
@@ -439,14 +445,14 @@ int fira_embed_rows_bwd(const int* ids, const void* d_out, float* d_emb, long ro
 
 int fira_ln_residual_fwd(const void* z, const void* resid, const float* gamma, const float* beta, void* outA,
                          void* outB, long split, float* mean, float* rstd, long rows, int dim, float p_drop,
-                         uint64_t seed, uint32_t stream_id, int dtype, void* stream) {
+                         uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "ln_residual_fwd: dim %d != 256", dim);
   FIRA_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, FIRA_ERR_ARG, "ln_residual_fwd: p_drop %f", p_drop);
   FIRA_CHECK_ARG(fira_aligned16(z) && fira_aligned16(resid) && fira_aligned16(outA) && fira_aligned16(outB),
                  FIRA_ERR_ALIGN, "ln_residual_fwd: 16-B alignment");
   if (rows == 0) return FIRA_OK;
   DISPATCH_T(dtype, ln_fwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
-      (const T*)z, (const T*)resid, gamma, beta, (T*)outA, (T*)outB, split, mean, rstd, rows, p_drop, seed, stream_id);)
+      (const T*)z, (const T*)resid, gamma, beta, (T*)outA, (T*)outB, split, mean, rstd, rows, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_ln_residual_fwd");
   return FIRA_OK;
 }
@@ -454,40 +460,40 @@ int fira_ln_residual_fwd(const void* z, const void* resid, const float* gamma, c
 int fira_ln_residual_bwd(const void* d_outA, const void* d_outB, long split, const void* z, const void* resid,
                          const float* mean, const float* rstd, const float* gamma, void* d_z, void* d_resid,
                          int d_resid_accum, float* d_gamma, float* d_beta, long rows, int dim, float p_drop,
-                         uint64_t seed, uint32_t stream_id, int dtype, void* stream) {
+                         uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "ln_residual_bwd: dim %d != 256", dim);
   if (rows == 0) return FIRA_OK;
   long g = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   int grid = (int)(g < 148L * 4 ? g : 148L * 4);   // few CTAs -> few d_gamma/d_beta atomics
   DISPATCH_T(dtype, ln_bwd_kernel<T><<<grid, CTA, 0, (cudaStream_t)stream>>>(
       (const T*)d_outA, (const T*)d_outB, split, (const T*)z, (const T*)resid, mean, rstd, gamma, (T*)d_z,
-      (T*)d_resid, d_resid_accum, d_gamma, d_beta, rows, p_drop, seed, stream_id);)
+      (T*)d_resid, d_resid_accum, d_gamma, d_beta, rows, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_ln_residual_bwd");
   return FIRA_OK;
 }
 
 int fira_comb_gate_fwd(const void* qk, long ld_qk, const float* vtab, const int* mark, void* out, long rows, int dim,
-                       int d_head, float p_drop, uint64_t seed, uint32_t stream_id, int dtype, void* stream) {
+                       int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "comb_gate_fwd: dim %d != 256", dim);
   FIRA_CHECK_ARG(ld_qk >= 2 * D && (ld_qk % 8) == 0, FIRA_ERR_SHAPE, "comb_gate_fwd: ld_qk %ld", ld_qk);
   if (rows == 0) return FIRA_OK;
   const float scale = 1.f / sqrtf((float)d_head);
   DISPATCH_T(dtype, comb_gate_fwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
-      (const T*)qk, ld_qk, vtab, mark, (T*)out, rows, scale, p_drop, seed, stream_id);)
+      (const T*)qk, ld_qk, vtab, mark, (T*)out, rows, scale, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate_fwd");
   return FIRA_OK;
 }
 
 int fira_comb_gate_bwd(const void* qk, long ld_qk, const float* vtab, const int* mark, const void* d_out, void* d_qk,
-                       float* d_vtab, long rows, int dim, int d_head, float p_drop, uint64_t seed, uint32_t stream_id,
-                       int dtype, void* stream) {
+                       float* d_vtab, long rows, int dim, int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr,
+                       uint32_t stream_id, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "comb_gate_bwd: dim %d != 256", dim);
   if (rows == 0) return FIRA_OK;
   const float scale = 1.f / sqrtf((float)d_head);
   long g = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   int grid = (int)(g < 148L * 4 ? g : 148L * 4);
   DISPATCH_T(dtype, comb_gate_bwd_kernel<T><<<grid, CTA, 0, (cudaStream_t)stream>>>(
-      (const T*)qk, ld_qk, vtab, mark, (const T*)d_out, (T*)d_qk, d_vtab, rows, scale, p_drop, seed, stream_id);)
+      (const T*)qk, ld_qk, vtab, mark, (const T*)d_out, (T*)d_qk, d_vtab, rows, scale, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate_bwd");
   return FIRA_OK;
 }

@@ -125,7 +125,8 @@ class FeedForward(_KernelBacked):
 
 def _run_cfg(module, stream_base=0):
     return {"training": module.training, "seed": ops.make_seed() if module.training else 0,
-            "stream_base": stream_base, "heads": module.num_head, "bf16": bool(getattr(module, "bf16", False))}
+            "stream_base": stream_base, "heads": module.num_head, "bf16": bool(getattr(module, "bf16", False)),
+            "seed_ctr": getattr(module, "seed_ctr", None)}
 
 
 class Encoder(nn.Module):

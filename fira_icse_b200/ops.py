@@ -121,8 +121,9 @@ def colsum(x, ld, M, N, weight=None, x_off=0, dtype=None):
 class Prec:
     """Precision context of one forward/backward pair: dtype codes, buffers, Linear dispatch."""
 
-    def __init__(self, bf16, wcache=None):
+    def __init__(self, bf16, wcache=None, seed_ctr=None):
         self.bf16 = bool(bf16)
+        self.seed_ctr = seed_ctr          # device uint64 counter added to the dropout seed (CUDA-graph replays)
         self.code = FIRA_BF16 if self.bf16 else FIRA_F32
         self.tdt = torch.bfloat16 if self.bf16 else torch.float32
         self.wcache = {} if wcache is None else wcache
@@ -172,7 +173,7 @@ class Prec:
     def ln_fwd(self, z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid):
         stats = torch.empty((2, rows), dtype=torch.float32, device=z.device)
         call("fira_ln_residual_fwd", _ptr(z), _ptr(resid), _ptr(gamma), _ptr(beta), _ptr(outA), _ptr(outB), split,
-             _ptr(stats), _ptr(stats, rows), rows, D, float(p), seed, sid, self.code, _stream())
+             _ptr(stats), _ptr(stats, rows), rows, D, float(p), seed, _ptr(self.seed_ctr), sid, self.code, _stream())
         return stats
 
     def ln_bwd(self, dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=None, accum=False):
@@ -181,8 +182,8 @@ class Prec:
             d_resid = torch.empty_like(z)
         dgb = torch.zeros((2, D), dtype=torch.float32, device=z.device)
         call("fira_ln_residual_bwd", _ptr(dA), _ptr(dB), split, _ptr(z), _ptr(resid), _ptr(stats), _ptr(stats, rows),
-             _ptr(gamma), _ptr(dz), _ptr(d_resid), int(accum), _ptr(dgb), _ptr(dgb, D), rows, D, float(p), seed, sid,
-             self.code, _stream())
+             _ptr(gamma), _ptr(dz), _ptr(d_resid), int(accum), _ptr(dgb), _ptr(dgb, D), rows, D, float(p), seed,
+             _ptr(self.seed_ctr), sid, self.code, _stream())
         return dz, d_resid, dgb[0], dgb[1]
 
 
@@ -229,7 +230,7 @@ class EncoderFn(torch.autograd.Function):
         p_comb = cfg["p_comb"] if training else 0.0
         p_gcn = cfg["p_gcn"] if training else 0.0
         heads = cfg["heads"]
-        pr = Prec(cfg.get("bf16", False))
+        pr = Prec(cfg.get("bf16", False), seed_ctr=cfg.get("seed_ctr"))
         dev = emb.device
         f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
@@ -250,7 +251,7 @@ class EncoderFn(torch.autograd.Function):
             Vtab = linear(mark_emb, Wv, bv)                            # fp32 [4, 256]: value has 4 distinct rows
             Cd = pr.empty((Mc, D), dev)
             call("fira_comb_gate_fwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(Cd), Mc, D, D // heads,
-                 float(p_comb), seed, sid + 0, pr.code, st)
+                 float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
             Zc = pr.linear(Cd, Wo, bo)
             st_c = pr.ln_fwd(Zc, Xc, clw, clb, Gin, Gin, Mc, Mc, p_comb, seed, sid + 1)   # -> Gin[:Mc]
             # ---- GCN (gnn_transformer.py:74-86)
@@ -284,7 +285,7 @@ class EncoderFn(torch.autograd.Function):
         R, Mc = B * N, B * n_code
         L = len(lp) // ENC_LAYER_PARAMS
         seed, heads = cfg["seed"], cfg["heads"]
-        pr = Prec(cfg.get("bf16", False), ctx.wcache)
+        pr = Prec(cfg.get("bf16", False), ctx.wcache, seed_ctr=cfg.get("seed_ctr"))
         dev = emb.device
         f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
@@ -324,7 +325,7 @@ class EncoderFn(torch.autograd.Function):
             dQK = pr.empty((Mc, 2 * D), dev)
             dVtab = torch.zeros((4, D), **f32)
             call("fira_comb_gate_bwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(dCd), _ptr(dQK), _ptr(dVtab),
-                 Mc, D, D // heads, float(p_comb), seed, sid + 0, pr.code, st)
+                 Mc, D, D // heads, float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
             d_bqk = colsum(dQK, 2 * D, Mc, 2 * D)
             d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D)
             pr.linear_dx(dQK, 2 * D, Wqk, Mc, out=dXc_n, accumulate=True)
@@ -361,7 +362,7 @@ class DecoderFn(torch.autograd.Function):
         H = cfg["heads"]
         training, seed = cfg["training"], cfg["seed"]
         p = cfg["p_dec"] if training else 0.0
-        pr = Prec(cfg.get("bf16", False))
+        pr = Prec(cfg.get("bf16", False), seed_ctr=cfg.get("seed_ctr"))
         dev = dec_emb.device
         f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
@@ -420,7 +421,7 @@ class DecoderFn(torch.autograd.Function):
         Mt, Ms = B * T, B * S
         L = len(lp) // DEC_LAYER_PARAMS
         H, seed = cfg["heads"], cfg["seed"]
-        pr = Prec(cfg.get("bf16", False), ctx.wcache)
+        pr = Prec(cfg.get("bf16", False), ctx.wcache, seed_ctr=cfg.get("seed_ctr"))
         dev = dec_emb.device
         st = _stream()
         ldkv = L * 2 * D

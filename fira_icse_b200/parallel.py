@@ -3,8 +3,8 @@
 The reference wraps the model in nn.DataParallel (run_model.py:392-394): one process, per-step
 parameter broadcast + gradient reduce to GPU 0, and the loss is sum(loss) / sum(tokens) over the
 gathered replicas (run_model.py:105).  Here every rank keeps its own replica and optimizer state;
-per step there is ONE all-reduce over a flat gradient bucket (the parameters' .grad tensors are views
-into it, so there is no pack/unpack copy) plus an 8-byte all-reduce of the token count so that the
+per step there is ONE all-reduce over a flat gradient bucket (one concatenation packs the gradients,
+afterwards the parameters' .grad tensors are views into the reduced buffer) plus an 8-byte all-reduce of the token count so that the
 loss is the same global token-weighted mean as upstream.  The 74 tensors that never receive
 gradients (encoder.lstm, encoder.combination_list1, gate_fc) are left out of the bucket.
 """
@@ -13,23 +13,31 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    """Flat fp32 buffer holding the gradients of `params`; each p.grad is a view into it."""
+    """Gradients of `params` as ONE flat fp32 buffer for the all-reduce.
+
+    Gradients are not pre-bound to the buffer: with `.grad = None` before backward autograd adopts
+    the tensors our Functions return (no zero-fill, no `grad += new` kernel per parameter -- 258 add
+    launches per step in the round-1 profile).  flatten() packs them with one concatenation;
+    after the all-reduce every `.grad` is re-pointed at its slice of the reduced buffer."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat = None
+
+    def zero(self):
+        for p in self.params:
+            p.grad = None
+
+    def flatten(self):
+        self.flat = torch.cat([p.grad.reshape(-1) for p in self.params])
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
-
-    def zero(self):
-        self.flat.zero_()
+        return self.flat
 
     def all_reduce(self, group=None, async_op=False):
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return dist.all_reduce(self.flatten(), op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
 class DataParallelStep:

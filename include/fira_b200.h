@@ -17,7 +17,9 @@
  *   - return 0 on success, a FIRA_ERR_* code otherwise; fira_last_error_string() describes the last
  *     failure on the calling thread; nothing throws or aborts across the boundary;
  *   - re-entrant, no hidden global state besides the per-thread error string;
- *   - dropout masks are a pure function of (seed, stream_id, element index): backward recomputes them.
+ *   - dropout masks are a pure function of (seed [+ *seed_ctr], stream_id, element index): backward
+ *     recomputes them; seed_ctr (device uint64, may be NULL) lets a captured CUDA graph draw fresh masks
+ *     on every replay by bumping the counter on the device.
  */
 #ifndef FIRA_B200_H_
 #define FIRA_B200_H_
@@ -77,19 +79,19 @@ int fira_embed_rows_bwd(const int* ids, const void* d_out, float* d_emb, long ro
  * rows to the next Combination without a torch.cat / slice copy). */
 int fira_ln_residual_fwd(const void* z, const void* resid, const float* gamma, const float* beta, void* outA,
                          void* outB, long split, float* mean, float* rstd, long rows, int dim, float p_drop,
-                         uint64_t seed, uint32_t stream_id, int dtype, void* stream);
+                         uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream);
 int fira_ln_residual_bwd(const void* d_outA, const void* d_outB, long split, const void* z, const void* resid,
                          const float* mean, const float* rstd, const float* gamma, void* d_z, void* d_resid,
                          int d_resid_accum, float* d_gamma, float* d_beta, long rows, int dim, float p_drop,
-                         uint64_t seed, uint32_t stream_id, int dtype, void* stream);
+                         uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream);
 
 /* ---- Combination gate (combination_layer.py:7-17): c = v + sigmoid(q*(k-v)/sqrt(d_head))*(k-v),
  *      dropout; qk = [q | k] per row, v = vtab[mark[row]] (4 x dim table = Linear(mark_embedding)). */
 int fira_comb_gate_fwd(const void* qk, long ld_qk, const float* vtab, const int* mark, void* out, long rows, int dim,
-                       int d_head, float p_drop, uint64_t seed, uint32_t stream_id, int dtype, void* stream);
+                       int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream);
 int fira_comb_gate_bwd(const void* qk, long ld_qk, const float* vtab, const int* mark, const void* d_out, void* d_qk,
-                       float* d_vtab, long rows, int dim, int d_head, float p_drop, uint64_t seed, uint32_t stream_id,
-                       int dtype, void* stream);
+                       float* d_vtab, long rows, int dim, int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr,
+                       uint32_t stream_id, int dtype, void* stream);
 
 /* d[i] = h[i] > 0 ? d[i] : 0  (backward of the FeedForward relu, gnn_transformer.py:172). */
 int fira_relu_bwd(const void* h, void* d, long n, int dtype, void* stream);

@@ -177,7 +177,7 @@ def test_comb_gate_fwd_bwd():
     out = torch.empty(rows, 256, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
     _lib.call("fira_comb_gate_fwd", qk.data_ptr(), 512, vtab.data_ptr(), mark.data_ptr(), out.data_ptr(), rows, 256,
-              32, 0.0, 0, 0, 0, st)
+              32, 0.0, 0, None, 0, 0, st)
     qkd, vd = qk.double().requires_grad_(True), vtab.double().requires_grad_(True)
     q, k, v = qkd[:, :256], qkd[:, 256:], vd[mark.long()]
     # reference formulation: softmax over the stacked pair (combination_layer.py:8-14)
@@ -189,18 +189,18 @@ def test_comb_gate_fwd_bwd():
     dqk = torch.empty(rows, 512, device=DEV)
     dv = torch.zeros(4, 256, device=DEV)
     _lib.call("fira_comb_gate_bwd", qk.data_ptr(), 512, vtab.data_ptr(), mark.data_ptr(), go.data_ptr(),
-              dqk.data_ptr(), dv.data_ptr(), rows, 256, 32, 0.0, 0, 0, 0, st)
+              dqk.data_ptr(), dv.data_ptr(), rows, 256, 32, 0.0, 0, None, 0, 0, st)
     close(dqk, qkd.grad, rtol=2e-5, atol=1e-5)
     close(dv, vd.grad, rtol=1e-4, atol=1e-4)
     # dropout: zeros of fwd and bwd coincide
     p = 0.1
     _lib.call("fira_comb_gate_fwd", qk.data_ptr(), 512, vtab.data_ptr(), mark.data_ptr(), out.data_ptr(), rows, 256,
-              32, p, 99, 3, 0, st)
+              32, p, 99, None, 3, 0, st)
     dropped = out == 0
     assert abs(dropped.float().mean().item() - p) < 0.01
     close(out[~dropped], (ref.detach() / (1 - p))[~dropped], rtol=1e-5, atol=1e-5)
     _lib.call("fira_comb_gate_bwd", qk.data_ptr(), 512, vtab.data_ptr(), mark.data_ptr(), go.data_ptr(),
-              dqk.data_ptr(), dv.data_ptr(), rows, 256, 32, p, 99, 3, 0, st)
+              dqk.data_ptr(), dv.data_ptr(), rows, 256, 32, p, 99, None, 3, 0, st)
     assert (dqk[:, :256][dropped] == 0).all() and (dqk[:, 256:][dropped] == 0).all()
 
 
@@ -465,6 +465,6 @@ def test_bad_arguments_return_error_codes_not_crashes():
         _lib.call("fira_relu_bwd", x.data_ptr(), x.data_ptr(), 7, 0, 0)
     with pytest.raises(_lib.FiraLibraryError):
         _lib.call("fira_ln_residual_fwd", x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(),
-                  x.data_ptr(), 0, None, None, 8, 128, 0.0, 0, 0, 0, 0)
+                  x.data_ptr(), 0, None, None, 8, 128, 0.0, 0, None, 0, 0, 0)
     with pytest.raises(_lib.FiraLibraryError, match="dtype"):
         _lib.call("fira_relu_bwd", x.data_ptr(), x.data_ptr(), 8, 9, 0)

@@ -45,7 +45,7 @@ def _worker(rank, world, port, q):
     dp = DataParallelStep(Toy(), lambda ps: torch.optim.SGD(ps, lr=0.1))
     loss, n = dp.step([x[lo:hi], w[lo:hi]])
     # plain python lists: tensors sent through a spawn Queue die with the sending process
-    q.put((rank, loss.item(), n.item(), dp.bucket.flat.tolist(), [p.detach().flatten().tolist() for p in dp.bucket.params],
+    q.put((rank, loss.item(), n.item(), torch.cat([p.grad.reshape(-1) for p in dp.bucket.params]).tolist(), [p.detach().flatten().tolist() for p in dp.bucket.params],
            dp.model.dead.weight.grad is None))
     dist.destroy_process_group()
 
