@@ -33,8 +33,10 @@ def test_graph_replay_equals_eager_training(precision):
     base.eval()                                   # dropout off -> deterministic comparison
     m_eager, m_graph = copy.deepcopy(base), copy.deepcopy(base)
     batches = [_packed(i * 8, i * 8 + 8) for i in range(4)]
-    dp = DataParallelStep(m_eager, lambda ps: torch.optim.Adam(ps, lr=1e-3))
-    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.Adam(ps, lr=1e-3, fused=True, capturable=True))
+    # plain SGD for the equality check: Adam's g/sqrt(v) turns fp32 summation-order noise on near-zero
+    # gradient entries into full +-lr steps (the Adam graph path is covered by the test below and by bench.py)
+    dp = DataParallelStep(m_eager, lambda ps: torch.optim.SGD(ps, lr=0.05))
+    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=0.05))
     # capture() warms up with 3 real optimizer steps on whatever is loaded: replicate them eagerly
     eng.load(batches[0])
     eng.capture(warmup=3)
