@@ -35,14 +35,14 @@ def test_graph_replay_equals_eager_training(precision):
     batches = [_packed(i * 8, i * 8 + 8) for i in range(4)]
     # plain SGD for the equality check: Adam's g/sqrt(v) turns fp32 summation-order noise on near-zero
     # gradient entries into full +-lr steps (the Adam graph path is covered by the test below and by bench.py)
-    dp = DataParallelStep(m_eager, lambda ps: torch.optim.SGD(ps, lr=0.05))
-    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=0.05))
+    dp = DataParallelStep(m_eager, lambda ps: torch.optim.SGD(ps, lr=2e-3))
+    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=2e-3))
     # capture() warms up with 3 real optimizer steps on whatever is loaded: replicate them eagerly
     eng.load(batches[0])
     eng.capture(warmup=3)
     for _ in range(3):
         dp.step(batches[0])
-    tol = 2e-3 if precision == "bf16" else 2e-4
+    tol = 5e-3 if precision == "bf16" else 2e-4
     for b in batches:
         loss_e, _ = dp.step(b)
         ls, n = eng.step(b)

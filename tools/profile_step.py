@@ -29,7 +29,8 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) a
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        k = e.name.split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:90]
+        k = e.name.replace("void ", "").replace("(anonymous namespace)::", "").replace("at::native::", "")
+        k = k.split("(")[0][:80]
         agg[k][0] += 1
         agg[k][1] += e.device_time
 tot = sum(v[1] for v in agg.values())
