@@ -37,3 +37,19 @@ tot = sum(v[1] for v in agg.values())
 print(f"precision={prec} B={B}: {sum(v[0] for v in agg.values())} kernels, {tot / 1e3:.2f} ms GPU time")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
     print(f"{t:9.1f} us {100 * t / tot:5.1f}% n={c:4d}  {k}")
+
+# per-launch detail for one kernel family (grid sizes come from the chrome trace)
+if len(sys.argv) > 3:
+    import json
+    import tempfile
+    pat = sys.argv[3]
+    path = os.path.join(tempfile.mkdtemp(), "trace.json")
+    prof.export_chrome_trace(path)
+    ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel" and pat in e.get("name", "")]
+    groups = collections.defaultdict(list)
+    for e in ev:
+        a = e.get("args", {})
+        groups[(tuple(a.get("grid", [])), tuple(a.get("block", [])))].append(e["dur"])
+    print(f"--- {pat}: {len(ev)} launches")
+    for k, v in sorted(groups.items(), key=lambda kv: -sum(kv[1])):
+        print(f"grid={k[0]} block={k[1]} n={len(v)} total={sum(v):8.1f} us  avg={sum(v) / len(v):7.1f}  min={min(v):7.1f} max={max(v):7.1f}")
