@@ -1,10 +1,16 @@
-// Multi-head attention core for the parity (fp32) path: one CTA per (batch, head) keeps K, V and the
-// 30 query rows of that head on chip (the whole problem fits in one SM's shared memory: Lq = 30,
-// Lk <= 370, d_head = 32).  gnn_transformer.py:144-156:
+// Multi-head attention core (gnn_transformer.py:144-156), one CTA per (commit, head):
 //     S = Q K^T / sqrt(d_head);  S[mask == 0] = -1e9;  P = softmax(S);  ctx = P V
-// mask = key padding (and causal for decoder self-attention, gnn_transformer.py:117).  No dropout on P.
-// Forward saves (row max, row sum) so backward recomputes P exactly instead of storing B*8*30*370 floats.
-// The throughput path (attention_tc.cu) does the two contractions on tcgen05 instead.
+// mask = key padding (and causal for decoder self-attention, gnn_transformer.py:117); no dropout on P.
+//
+// The problem is tiny (Lq = 30, Lk <= 370, d_head = 32) and mostly padding: on the DataSet only ~127 of the
+// 370 memory rows are real.  exp(-1e9 - max) is exactly 0 in fp32, so masked keys contribute nothing --
+// the kernels COMPACT the valid keys first (ballot scan into a shared index list) and only load / multiply
+// those (3x less work on real data, bit-for-bit the same sums).  A fully masked row (all keys padded)
+// keeps the reference's behaviour: uniform P over all keys, no gradient to the scores.
+// Each warp handles two query rows at a time so every K / V shared-memory read feeds two rows.
+// Forward saves (row max, row sum); backward recomputes P from them, gets delta = rowsum(P * dP) as
+// dO . O (so keys can be processed in chunks of 128 with a small shared-memory footprint, 3 CTAs/SM)
+// and writes zero gradients for the masked keys.
 #include "common.cuh"
 #include "fira_b200.h"
 
@@ -13,6 +19,9 @@ namespace {
 constexpr int DH = 32;           // head dim (256 / 8)
 constexpr int KPAD = DH + 1;     // conflict-free column reads of K/V tiles
 constexpr int NWARPS = 8;
+constexpr int NTHR = NWARPS * 32;
+constexpr int KC = 128;          // keys per backward chunk
+constexpr int LQ_MAX = 32;       // tar_len 30 (run_model.py:32)
 
 struct AttnArgs {
   const void* q; long ldq;       // row (b*Lq + t), head h at column h*32
@@ -24,156 +33,224 @@ struct AttnArgs {
   float scale;
 };
 
+// 16-byte loads of a 32-wide head slice; row index taken from `rows_idx` (compacted keys) or identity
 template <typename T>
-__device__ __forceinline__ void load_tile(float* dst, const T* src, long ld, int rows, int tid, int nthr) {
-  // rows x 32 -> dst[row][KPAD].  16-byte loads (a head slice of a row is 128 B fp32 / 64 B bf16), several
-  // independent loads in flight per thread: the scalar version of round 1 was latency-bound (one 4-byte
-  // load per thread per trip, ~40 us per 370-row tile).
-  constexpr int EPV = 16 / sizeof(T);          // elements per 16-byte vector
-  constexpr int VPR = DH / EPV;                // vectors per row
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld * sizeof(T)) % 16 == 0);
-  if (vec_ok) {
+__device__ __forceinline__ void load_rows(float* dst, const T* src, long ld, const int* rows_idx, int row0, int nrows) {
+  constexpr int EPV = 16 / sizeof(T);
+  constexpr int VPR = DH / EPV;
 #pragma unroll 4
-    for (int idx = tid; idx < rows * VPR; idx += nthr) {
-      const int r = idx / VPR, c = idx % VPR;
-      const uint4 raw = *reinterpret_cast<const uint4*>(src + (long)r * ld + c * EPV);
-      float* o = dst + r * KPAD + c * EPV;
-      if constexpr (sizeof(T) == 4) {
-        o[0] = __uint_as_float(raw.x); o[1] = __uint_as_float(raw.y);
-        o[2] = __uint_as_float(raw.z); o[3] = __uint_as_float(raw.w);
-      } else {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  for (int idx = threadIdx.x; idx < nrows * VPR; idx += NTHR) {
+    const int j = idx / VPR, c = idx % VPR;
+    const int r = rows_idx ? rows_idx[row0 + j] : row0 + j;
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + (long)r * ld + c * EPV);
+    float* o = dst + j * KPAD + c * EPV;
+    if constexpr (sizeof(T) == 4) {
+      o[0] = __uint_as_float(raw.x); o[1] = __uint_as_float(raw.y);
+      o[2] = __uint_as_float(raw.z); o[3] = __uint_as_float(raw.w);
+    } else {
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); o[2 * q] = f.x; o[2 * q + 1] = f.y; }
-      }
-    }
-  } else {
-    for (int idx = tid; idx < rows * DH; idx += nthr) {
-      int r = idx / DH, d = idx % DH;
-      dst[r * KPAD + d] = Act<T>::ld(src + (long)r * ld + d);
+      for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hh[q]); o[2 * q] = f.x; o[2 * q + 1] = f.y; }
     }
   }
 }
 
+// valid-key compaction by warp 0: kidx[0..nv) = original indices of keys with mask == 1 (ascending).
+// nv == 0 (every key padded): identity list of all keys and *filled = 1 (scores are all -1e9 -> uniform P).
+// causal (self-attention, Lk = 30): no compaction -- a row whose every permitted key is padding must stay
+// uniform over ALL keys like the reference, so padding is handled by the score mask instead.
+__device__ __forceinline__ void compact_keys(const unsigned char* km, int Lk, int causal, int* kidx, int* nv_out,
+                                             int* filled) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int n = 0;
+    for (int s0 = 0; s0 < Lk && !causal; s0 += 32) {
+      const int s = s0 + lane;
+      const bool ok = s < Lk && km[s] != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) kidx[n + __popc(bal & ((1u << lane) - 1u))] = s;
+      n += __popc(bal);
+    }
+    if (n == 0) {
+      for (int s = lane; s < Lk; s += 32) kidx[s] = s;
+      n = Lk;
+      if (lane == 0) *filled = causal ? 0 : 1;
+    } else if (lane == 0) *filled = 0;
+    if (lane == 0) *nv_out = n;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ forward
 template <typename T>
-__global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(AttnArgs a, T* __restrict__ ctx, long ldo,
-                                                               float* __restrict__ stats /* [B,H,Lq,2] */) {
+__global__ void __launch_bounds__(NTHR) attn_fwd_kernel(AttnArgs a, T* __restrict__ ctx, long ldo,
+                                                        float* __restrict__ stats /* [B,H,Lq,2] */) {
   extern __shared__ float smem[];
+  __shared__ int nv_s, filled_s;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* Ks = smem;                         // [Lk][KPAD]
-  float* Vs = Ks + a.Lk * KPAD;             // [Lk][KPAD]
-  float* Qs = Vs + a.Lk * KPAD;             // [Lq][KPAD]
-  float* Ps = Qs + a.Lq * KPAD;             // [NWARPS][Lk]
-  load_tile(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, a.Lk, threadIdx.x, blockDim.x);
-  load_tile(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, a.Lk, threadIdx.x, blockDim.x);
-  load_tile(Qs, (const T*)a.q + (long)b * a.Lq * a.ldq + h * DH, a.ldq, a.Lq, threadIdx.x, blockDim.x);
-  __syncthreads();
+  float* Ks = smem;                          // [Lk][KPAD]   (first nv rows used)
+  float* Vs = Ks + a.Lk * KPAD;              // [Lk][KPAD]
+  float* Qs = Vs + a.Lk * KPAD;              // [Lq][KPAD]
+  float* Ps = Qs + a.Lq * KPAD;              // [NWARPS][2][Lk]
+  int* kidx = reinterpret_cast<int*>(Ps + NWARPS * 2 * a.Lk);   // [Lk]
+  compact_keys(a.key_mask + (long)b * a.Lk, a.Lk, a.causal, kidx, &nv_s, &filled_s);
   const unsigned char* km = a.key_mask + (long)b * a.Lk;
-  float* P = Ps + warp * a.Lk;
-  for (int t = warp; t < a.Lq; t += NWARPS) {
-    float qreg[DH];
+  const int nv = nv_s;
+  const bool filled = filled_s != 0;
+  load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, 0, nv);
+  load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, 0, nv);
+  load_rows(Qs, (const T*)a.q + (long)b * a.Lq * a.ldq + h * DH, a.ldq, nullptr, 0, a.Lq);
+  __syncthreads();
+  float* P0 = Ps + (warp * 2 + 0) * a.Lk;
+  float* P1 = Ps + (warp * 2 + 1) * a.Lk;
+  for (int t0 = warp * 2; t0 < a.Lq; t0 += NWARPS * 2) {
+    const int t1 = min(t0 + 1, a.Lq - 1);                // odd Lq: row duplicated, second result dropped
+    float q0[DH], q1[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) qreg[d] = Qs[t * KPAD + d];
-    float mx = -INFINITY;
-    for (int s = lane; s < a.Lk; s += 32) {
-      float acc = 0.f;
+    for (int d = 0; d < DH; ++d) { q0[d] = Qs[t0 * KPAD + d]; q1[d] = Qs[t1 * KPAD + d]; }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    for (int j = lane; j < nv; j += 32) {
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) acc = fmaf(qreg[d], Ks[s * KPAD + d], acc);
-      acc *= a.scale;
-      const bool ok = km[s] && (!a.causal || s <= t);
-      acc = ok ? acc : kMaskFill;
-      P[s] = acc;
-      mx = fmaxf(mx, acc);
+      for (int d = 0; d < DH; ++d) { const float kd = Ks[j * KPAD + d]; s0 = fmaf(q0[d], kd, s0); s1 = fmaf(q1[d], kd, s1); }
+      const int ko = kidx[j];
+      const bool pad = filled || (a.causal && km[ko] == 0);
+      s0 = (pad || (a.causal && ko > t0)) ? kMaskFill : s0 * a.scale;
+      s1 = (pad || (a.causal && ko > t1)) ? kMaskFill : s1 * a.scale;
+      P0[j] = s0; P1[j] = s1;
+      mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int s = lane; s < a.Lk; s += 32) { float e = expf(P[s] - mx); P[s] = e; sum += e; }
-    sum = warp_sum(sum);
+    mx0 = warp_max(mx0); mx1 = warp_max(mx1);
+    float sum0 = 0.f, sum1 = 0.f;
+    for (int j = lane; j < nv; j += 32) {
+      const float e0 = expf(P0[j] - mx0), e1 = expf(P1[j] - mx1);
+      P0[j] = e0; P1[j] = e1; sum0 += e0; sum1 += e1;
+    }
+    sum0 = warp_sum(sum0); sum1 = warp_sum(sum1);
     __syncwarp();
-    const float inv = 1.f / sum;
-    float o = 0.f;
-    for (int s = 0; s < a.Lk; ++s) o = fmaf(P[s], Vs[s * KPAD + lane], o);
-    Act<T>::st(ctx + ((long)b * a.Lq + t) * ldo + h * DH + lane, o * inv);
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < nv; ++j) { const float vv = Vs[j * KPAD + lane]; o0 = fmaf(P0[j], vv, o0); o1 = fmaf(P1[j], vv, o1); }
+    Act<T>::st(ctx + ((long)b * a.Lq + t0) * ldo + h * DH + lane, o0 / sum0);
+    if (t1 != t0) Act<T>::st(ctx + ((long)b * a.Lq + t1) * ldo + h * DH + lane, o1 / sum1);
     if (lane == 0 && stats) {
-      float* st = stats + (((long)b * a.H + h) * a.Lq + t) * 2;
-      st[0] = mx; st[1] = sum;
+      float* st = stats + (((long)b * a.H + h) * a.Lq + t0) * 2;
+      st[0] = mx0; st[1] = sum0;
+      if (t1 != t0) { st[2] = mx1; st[3] = sum1; }
     }
     __syncwarp();
   }
 }
 
-// Backward: dV = P^T dO, dP = dO V^T, dS = P * (dP - rowsum(P*dP)), dQ = scale dS K, dK = scale dS^T Q.
+// ------------------------------------------------------------------------------------------------ backward
+// dV = P^T dO, dP = dO V^T, dS = P * (dP - delta), delta = dO . O, dQ = scale dS K, dK = scale dS^T Q.
 template <typename T>
-__global__ void __launch_bounds__(NWARPS * 32) attn_bwd_kernel(AttnArgs a, const T* __restrict__ d_ctx, long ldo,
-                                                               const float* __restrict__ stats, T* __restrict__ dq,
-                                                               long lddq, T* __restrict__ dk, long lddk,
-                                                               T* __restrict__ dv, long lddv) {
+__global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __restrict__ out, const T* __restrict__ d_ctx,
+                                                        long ldo, const float* __restrict__ stats, T* __restrict__ dq,
+                                                        long lddq, T* __restrict__ dk, long lddk, T* __restrict__ dv,
+                                                        long lddv) {
   extern __shared__ float smem[];
+  __shared__ int nv_s, filled_s;
+  __shared__ float delta_s[LQ_MAX], mx_s[LQ_MAX], inv_s[LQ_MAX];
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int LkP = a.Lk + 1;
-  float* Ks = smem;                         // [Lk][KPAD]
-  float* Vs = Ks + a.Lk * KPAD;             // [Lk][KPAD]
-  float* Qs = Vs + a.Lk * KPAD;             // [Lq][KPAD]
-  float* Os = Qs + a.Lq * KPAD;             // [Lq][KPAD]   dO
-  float* Pm = Os + a.Lq * KPAD;             // [Lq][LkP]    P
-  float* Sm = Pm + a.Lq * LkP;              // [Lq][LkP]    dS
-  load_tile(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, a.Lk, threadIdx.x, blockDim.x);
-  load_tile(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, a.Lk, threadIdx.x, blockDim.x);
-  load_tile(Qs, (const T*)a.q + (long)b * a.Lq * a.ldq + h * DH, a.ldq, a.Lq, threadIdx.x, blockDim.x);
-  load_tile(Os, d_ctx + (long)b * a.Lq * ldo + h * DH, ldo, a.Lq, threadIdx.x, blockDim.x);
-  __syncthreads();
+  constexpr int PP = KC + 1;
+  float* Ks = smem;                          // [KC][KPAD]
+  float* Vs = Ks + KC * KPAD;                // [KC][KPAD]
+  float* Qs = Vs + KC * KPAD;                // [Lq][KPAD]
+  float* Os = Qs + a.Lq * KPAD;              // [Lq][KPAD]  dO
+  float* Pm = Os + a.Lq * KPAD;              // [Lq][PP]    P
+  float* Sm = Pm + a.Lq * PP;                // [Lq][PP]    dS
+  int* kidx = reinterpret_cast<int*>(Sm + a.Lq * PP);   // [Lk]
   const unsigned char* km = a.key_mask + (long)b * a.Lk;
+  compact_keys(km, a.Lk, a.causal, kidx, &nv_s, &filled_s);
+  const int nv = nv_s;
+  const bool filled = filled_s != 0;
+  // delta_t = dO_t . O_t  (== sum_s P dP), row statistics
+  load_rows(Qs, out + (long)b * a.Lq * ldo + h * DH, ldo, nullptr, 0, a.Lq);       // O, temporarily in Qs
+  load_rows(Os, d_ctx + (long)b * a.Lq * ldo + h * DH, ldo, nullptr, 0, a.Lq);
+  __syncthreads();
   for (int t = warp; t < a.Lq; t += NWARPS) {
-    float qreg[DH], oreg[DH];
-#pragma unroll
-    for (int d = 0; d < DH; ++d) { qreg[d] = Qs[t * KPAD + d]; oreg[d] = Os[t * KPAD + d]; }
-    const float* st = stats + (((long)b * a.H + h) * a.Lq + t) * 2;
-    const float mx = st[0], inv = 1.f / st[1];
-    float delta = 0.f;
-    for (int s = lane; s < a.Lk; s += 32) {
-      float acc = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) {
-        acc = fmaf(qreg[d], Ks[s * KPAD + d], acc);
-        dp = fmaf(oreg[d], Vs[s * KPAD + d], dp);
-      }
-      acc *= a.scale;
-      const bool ok = km[s] && (!a.causal || s <= t);
-      acc = ok ? acc : kMaskFill;
-      const float p = expf(acc - mx) * inv;
-      Pm[t * LkP + s] = p;
-      Sm[t * LkP + s] = dp;
-      delta = fmaf(p, dp, delta);
+    const float x = warp_sum(Qs[t * KPAD + lane] * Os[t * KPAD + lane]);
+    if (lane == 0) {
+      delta_s[t] = x;
+      const float* st = stats + (((long)b * a.H + h) * a.Lq + t) * 2;
+      mx_s[t] = st[0]; inv_s[t] = 1.f / st[1];
     }
-    delta = warp_sum(delta);
-    // masked_fill overwrote the masked scores: no gradient reaches them even when P != 0 there
-    // (a fully masked row has uniform P)
-    for (int s = lane; s < a.Lk; s += 32) {
-      const bool ok = km[s] && (!a.causal || s <= t);
-      Sm[t * LkP + s] = ok ? Pm[t * LkP + s] * (Sm[t * LkP + s] - delta) : 0.f;
-    }
-    __syncwarp();
-    float g = 0.f;   // dQ[t][lane]
-    for (int s = 0; s < a.Lk; ++s) g = fmaf(Sm[t * LkP + s], Ks[s * KPAD + lane], g);
-    Act<T>::st(dq + ((long)b * a.Lq + t) * lddq + h * DH + lane, g * a.scale);
   }
   __syncthreads();
-  for (int s = warp; s < a.Lk; s += NWARPS) {
-    float gk = 0.f, gv = 0.f;
-    for (int t = 0; t < a.Lq; ++t) {
-      gk = fmaf(Sm[t * LkP + s], Qs[t * KPAD + lane], gk);
-      gv = fmaf(Pm[t * LkP + s], Os[t * KPAD + lane], gv);
+  load_rows(Qs, (const T*)a.q + (long)b * a.Lq * a.ldq + h * DH, a.ldq, nullptr, 0, a.Lq);
+  float dqa[(LQ_MAX + NWARPS - 1) / NWARPS];   // dQ[t][lane] for this warp's rows t = warp + 8*i
+#pragma unroll
+  for (int i = 0; i < (LQ_MAX + NWARPS - 1) / NWARPS; ++i) dqa[i] = 0.f;
+
+  for (int c0 = 0; c0 < nv; c0 += KC) {
+    const int nc = min(KC, nv - c0);
+    __syncthreads();                                     // previous chunk fully consumed (and Qs loaded)
+    load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, c0, nc);
+    load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, c0, nc);
+    __syncthreads();
+    // ---- phase A: P, dS for the warp's query rows; dQ accumulation
+#pragma unroll
+    for (int i = 0; i < (LQ_MAX + NWARPS - 1) / NWARPS; ++i) {
+      const int t = warp + i * NWARPS;
+      if (t < a.Lq) {
+        float qr[DH], orr[DH];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { qr[d] = Qs[t * KPAD + d]; orr[d] = Os[t * KPAD + d]; }
+        const float mx = mx_s[t], inv = inv_s[t], dl = delta_s[t];
+        for (int j = lane; j < nc; j += 32) {
+          float sc = 0.f, dp = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) { sc = fmaf(qr[d], Ks[j * KPAD + d], sc); dp = fmaf(orr[d], Vs[j * KPAD + d], dp); }
+          const bool masked = filled || (a.causal && (kidx[c0 + j] > t || km[kidx[c0 + j]] == 0));
+          sc = masked ? kMaskFill : sc * a.scale;
+          const float pr = expf(sc - mx) * inv;
+          Pm[t * PP + j] = pr;
+          Sm[t * PP + j] = masked ? 0.f : pr * (dp - dl);      // masked_fill blocks the gradient
+        }
+        __syncwarp();
+        float g = 0.f;
+        for (int j = 0; j < nc; ++j) g = fmaf(Sm[t * PP + j], Ks[j * KPAD + lane], g);
+        dqa[i] += g;
+      }
     }
-    Act<T>::st(dk + ((long)b * a.Lk + s) * lddk + h * DH + lane, gk * a.scale);
-    Act<T>::st(dv + ((long)b * a.Lk + s) * lddv + h * DH + lane, gv);
+    __syncthreads();
+    // ---- phase B: dK, dV rows of this chunk (written at the keys' original positions)
+    for (int j = warp; j < nc; j += NWARPS) {
+      float gk = 0.f, gv = 0.f;
+      for (int t = 0; t < a.Lq; ++t) {
+        gk = fmaf(Sm[t * PP + j], Qs[t * KPAD + lane], gk);
+        gv = fmaf(Pm[t * PP + j], Os[t * KPAD + lane], gv);
+      }
+      const long row = (long)b * a.Lk + kidx[c0 + j];
+      Act<T>::st(dk + row * lddk + h * DH + lane, gk * a.scale);
+      Act<T>::st(dv + row * lddv + h * DH + lane, gv);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < (LQ_MAX + NWARPS - 1) / NWARPS; ++i) {
+    const int t = warp + i * NWARPS;
+    if (t < a.Lq) Act<T>::st(dq + ((long)b * a.Lq + t) * lddq + h * DH + lane, dqa[i] * a.scale);
+  }
+  // masked keys receive exactly zero gradient
+  if (!filled && !a.causal) {
+    for (int s = warp; s < a.Lk; s += NWARPS) {
+      if (km[s] == 0) {
+        const long row = (long)b * a.Lk + s;
+        Act<T>::st(dk + row * lddk + h * DH + lane, 0.f);
+        Act<T>::st(dv + row * lddv + h * DH + lane, 0.f);
+      }
+    }
   }
 }
 
-size_t fwd_smem(int Lq, int Lk) { return sizeof(float) * ((size_t)2 * Lk * KPAD + (size_t)Lq * KPAD + (size_t)NWARPS * Lk); }
+size_t fwd_smem(int Lq, int Lk) {
+  return sizeof(float) * ((size_t)2 * Lk * KPAD + (size_t)Lq * KPAD + (size_t)NWARPS * 2 * Lk) + sizeof(int) * (size_t)Lk;
+}
 size_t bwd_smem(int Lq, int Lk) {
-  return sizeof(float) * ((size_t)2 * Lk * KPAD + (size_t)2 * Lq * KPAD + (size_t)2 * Lq * (Lk + 1));
+  return sizeof(float) * ((size_t)2 * KC * KPAD + (size_t)2 * Lq * KPAD + (size_t)2 * Lq * (KC + 1)) +
+         sizeof(int) * (size_t)Lk;
 }
 
 template <typename K>
@@ -189,6 +266,15 @@ int set_smem(K kernel, size_t bytes, const char* name) {
   return FIRA_OK;
 }
 
+int check_layout(const char* name, const void* p, long ld, int dtype) {
+  const long esz = dtype == FIRA_F32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (ld * esz) % 16 != 0) {
+    fira_set_error(FIRA_ERR_ALIGN, "%s: operands must be 16-B aligned with 16-B row pitch", name);
+    return FIRA_ERR_ALIGN;
+  }
+  return FIRA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -199,39 +285,48 @@ int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* 
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_fwd: d_head %d != 32", d_head);
   FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, FIRA_ERR_SHAPE, "attn_fwd: shape");
   FIRA_CHECK_ARG(!causal || Lq == Lk, FIRA_ERR_SHAPE, "attn_fwd: causal needs Lq == Lk");
+  FIRA_CHECK_ARG(dtype == FIRA_F32 || dtype == FIRA_BF16, FIRA_ERR_DTYPE, "attn_fwd: dtype %d", dtype);
+  int rc;
+  if ((rc = check_layout("attn_fwd", q, ldq, dtype)) || (rc = check_layout("attn_fwd", k, ldk, dtype)) ||
+      (rc = check_layout("attn_fwd", v, ldv, dtype)))
+    return rc;
   AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = fwd_smem(Lq, Lk);
-  int rc;
   if (dtype == FIRA_F32) {
     if ((rc = set_smem(attn_fwd_kernel<float>, smem, "attn_fwd"))) return rc;
-    attn_fwd_kernel<float><<<B * H, NWARPS * 32, smem, (cudaStream_t)stream>>>(a, (float*)ctx, ldo, stats);
-  } else if (dtype == FIRA_BF16) {
+    attn_fwd_kernel<float><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(a, (float*)ctx, ldo, stats);
+  } else {
     if ((rc = set_smem(attn_fwd_kernel<__nv_bfloat16>, smem, "attn_fwd"))) return rc;
-    attn_fwd_kernel<__nv_bfloat16><<<B * H, NWARPS * 32, smem, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)ctx, ldo, stats);
-  } else { fira_set_error(FIRA_ERR_DTYPE, "attn_fwd: dtype %d", dtype); return FIRA_ERR_DTYPE; }
+    attn_fwd_kernel<__nv_bfloat16><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)ctx, ldo, stats);
+  }
   FIRA_CHECK_LAUNCH("fira_attn_fwd");
   return FIRA_OK;
 }
 
 int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                  const unsigned char* key_mask, int causal, const void* d_ctx, long ldo, const float* stats, void* dq,
-                  long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H, int Lq, int Lk, int d_head,
-                  int dtype, void* stream) {
+                  const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
+                  const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
+                  int Lq, int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_bwd: d_head %d != 32", d_head);
-  FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, FIRA_ERR_SHAPE, "attn_bwd: shape");
+  FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lq <= LQ_MAX, FIRA_ERR_SHAPE, "attn_bwd: shape (Lq <= 32)");
+  FIRA_CHECK_ARG(dtype == FIRA_F32 || dtype == FIRA_BF16, FIRA_ERR_DTYPE, "attn_bwd: dtype %d", dtype);
+  int rc;
+  if ((rc = check_layout("attn_bwd", q, ldq, dtype)) || (rc = check_layout("attn_bwd", k, ldk, dtype)) ||
+      (rc = check_layout("attn_bwd", v, ldv, dtype)) || (rc = check_layout("attn_bwd", ctx, ldo, dtype)) ||
+      (rc = check_layout("attn_bwd", d_ctx, ldo, dtype)))
+    return rc;
   AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = bwd_smem(Lq, Lk);
-  int rc;
   if (dtype == FIRA_F32) {
     if ((rc = set_smem(attn_bwd_kernel<float>, smem, "attn_bwd"))) return rc;
-    attn_bwd_kernel<float><<<B * H, NWARPS * 32, smem, (cudaStream_t)stream>>>(
-        a, (const float*)d_ctx, ldo, stats, (float*)dq, lddq, (float*)dk, lddk, (float*)dv, lddv);
-  } else if (dtype == FIRA_BF16) {
+    attn_bwd_kernel<float><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(
+        a, (const float*)ctx, (const float*)d_ctx, ldo, stats, (float*)dq, lddq, (float*)dk, lddk, (float*)dv, lddv);
+  } else {
     if ((rc = set_smem(attn_bwd_kernel<__nv_bfloat16>, smem, "attn_bwd"))) return rc;
-    attn_bwd_kernel<__nv_bfloat16><<<B * H, NWARPS * 32, smem, (cudaStream_t)stream>>>(
-        a, (const __nv_bfloat16*)d_ctx, ldo, stats, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk,
-        (__nv_bfloat16*)dv, lddv);
-  } else { fira_set_error(FIRA_ERR_DTYPE, "attn_bwd: dtype %d", dtype); return FIRA_ERR_DTYPE; }
+    attn_bwd_kernel<__nv_bfloat16><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(
+        a, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)d_ctx, ldo, stats, (__nv_bfloat16*)dq, lddq,
+        (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv);
+  }
   FIRA_CHECK_LAUNCH("fira_attn_bwd");
   return FIRA_OK;
 }

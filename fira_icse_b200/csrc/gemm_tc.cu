@@ -202,8 +202,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     const bool first = blockIdx.z == 0;
     const int mrow0 = m0 + quarter * 32;
+    if (p.splits > 1) {
+      // split-K partials: lane <-> consecutive columns, so every RED.ADD of a warp covers one 128-B line
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = mrow0 + rr;
+        if (m >= p.M) break;
+        const float rsm = (p.rs && first) ? p.rs[m] : 0.f;
+        float* crow = (float*)p.C + (long)m * p.ldc;
+#pragma unroll
+        for (int jg = 0; jg < BN / 32; ++jg) {
+          const int n = n0 + jg * 32 + lane;
+          if (n < p.N) {
+            float x = stg[(size_t)rr * PITCH + jg * 32 + lane];
+            if (first) {
+              if (p.bias) x += p.bias[n];
+              if (p.rs) x = fmaf(rsm, p.rc[n], x);
+            }
+            atomicAdd(crow + n, x);
+          }
+        }
+      }
+    }
     const int col = lane * 8;
-    if (col < BN) {
+    if (p.splits <= 1 && col < BN) {
       const int n = n0 + col;
       float bv[8], rcv[8];
 #pragma unroll

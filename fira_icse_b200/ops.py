@@ -107,7 +107,7 @@ def _tc_splits(tiles, kblocks):
     """split-K factor that brings a small-output GEMM to ~2 CTAs per SM"""
     if tiles >= 148:
         return 1
-    return max(1, min(kblocks // 4 if kblocks >= 8 else 1, _ceil(296, tiles)))
+    return max(1, min(kblocks // 8 if kblocks >= 16 else 1, _ceil(148, tiles)))
 
 
 def colsum(x, ld, M, N, weight=None, x_off=0, dtype=None):
@@ -451,7 +451,7 @@ class DecoderFn(torch.autograd.Function):
             dctx2 = pr.linear_dx(dZ2, D, cWo, Mt)
             dQ = pr.empty((Mt, D), dev)
             call("fira_attn_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
-                 _ptr(mem_mask), 0, _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
+                 _ptr(mem_mask), 0, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
                  _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
             d_cbq = colsum(dQ, D, Mt, D)
             d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D)
@@ -463,7 +463,7 @@ class DecoderFn(torch.autograd.Function):
             dctx1 = pr.linear_dx(dZ1, D, sWo, Mt)
             dQKV = pr.empty((Mt, 3 * D), dev)
             call("fira_attn_bwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
-                 _ptr(dctx1), D, _ptr(st1), _ptr(dQKV), 3 * D, _ptr(dQKV, D), 3 * D, _ptr(dQKV, 2 * D), 3 * D,
+                 _ptr(ctx1), _ptr(dctx1), D, _ptr(st1), _ptr(dQKV), 3 * D, _ptr(dQKV, D), 3 * D, _ptr(dQKV, 2 * D), 3 * D,
                  B, H, T, T, D // H, pr.code, st)
             d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D)
             d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D)

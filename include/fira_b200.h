@@ -117,14 +117,15 @@ int fira_csr_rowsum(const int* rowptr, const float* val, int B, int n_code, int 
 int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, const void* x, const void* addend,
                        void* y, int B, int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream);
 
-/* ---- attention core (gnn_transformer.py:144-156); stats = (row max, row sum) [B,H,Lq,2]. */
+/* ---- attention core (gnn_transformer.py:144-156); stats = (row max, row sum) [B,H,Lq,2];
+ *      backward also takes the forward output `ctx` (same layout as d_ctx): delta = dO . O. */
 int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
                   const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
                   int Lk, int d_head, int dtype, void* stream);
 int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                  const unsigned char* key_mask, int causal, const void* d_ctx, long ldo, const float* stats, void* dq,
-                  long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H, int Lq, int Lk, int d_head,
-                  int dtype, void* stream);
+                  const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
+                  const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
+                  int Lq, int Lk, int d_head, int dtype, void* stream);
 
 /* ---- CopyNet scores (Model.py:17-18): sc[b,t,s] = b_res + w_res . tanh(src[b,s] + tgt[b,t]). */
 int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res, float* scores,

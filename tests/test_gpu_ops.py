@@ -306,7 +306,7 @@ def test_attention_fwd_bwd(Lk, causal):
     dq = torch.empty_like(q)
     dkv = torch.zeros_like(kv)
     _lib.call("fira_attn_bwd", q.data_ptr(), Dm, kv.data_ptr(), ld, kv.data_ptr() + voff * 4, ld, mask_u8.data_ptr(),
-              causal, go.data_ptr(), Dm, stats.data_ptr(), dq.data_ptr(), Dm, dkv.data_ptr(), ld,
+              causal, ctx.data_ptr(), go.data_ptr(), Dm, stats.data_ptr(), dq.data_ptr(), Dm, dkv.data_ptr(), ld,
               dkv.data_ptr() + voff * 4, ld, B, H, Lq, Lk, dh, 0, st)
     close(dq, qd.grad, rtol=5e-5, atol=1e-5)
     close(dkv, kvd.grad, rtol=5e-5, atol=1e-5)
