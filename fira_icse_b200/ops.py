@@ -199,6 +199,39 @@ def ln_bwd(dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=No
     return _F32.ln_bwd(dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=d_resid, accum=accum)
 
 
+_SIDE_STREAMS = {}
+
+
+class Fork:
+    """Runs the weight-gradient / bias-gradient work of a backward pass on a side stream.
+
+    In a backward step `dZ` feeds three independent consumers: the input-gradient GEMM (critical
+    path), the weight-gradient GEMM and the bias column sums.  The last two use a handful of CTAs
+    each; issued on a second stream they overlap with the critical path (and become parallel
+    branches when the step is captured into a CUDA graph).  Tensors read on the side stream are kept
+    alive until join(), tensors produced there are only consumed after join()."""
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        self.side = _SIDE_STREAMS[key]
+        self.keep = []
+        self.used = False
+
+    def __call__(self, *tensors):
+        self.keep.extend(tensors)
+        self.side.wait_stream(self.main)
+        self.used = True
+        return torch.cuda.stream(self.side)
+
+    def join(self):
+        if self.used:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
 def make_seed():
     """64-bit dropout seed drawn from torch's CPU generator (so torch.manual_seed controls it)."""
     return int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -296,42 +329,47 @@ class EncoderFn(torch.autograd.Function):
         call("fira_unpack_memory", _ptr(d_mem), _ptr(dXc), _ptr(dGin), B, n_code, n_sub, n_ast, D, pr.code, st)
         d_mark_emb = torch.zeros_like(mark_emb)
         grads = [None] * len(lp)
+        fork = Fork(dev)
         for i in reversed(range(L)):
             Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
             Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1 = ctx.saved[i]
             sid = cfg["stream_base"] + i * 8
             # ---- GCN backward
             dZ, dRes, d_glw, d_glb = pr.ln_bwd(dXc, dGin, Mc, Z, Gin, st_g, glw, R, p_gcn, seed, sid + 2)
-            d_b2 = colsum(dZ, D, R, D)
-            d_c1 = colsum(dZ, D, R, D, weight=rs)
-            dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
+            with fork(dZ, G, rs, W1, W2, b1):
+                d_b2 = colsum(dZ, D, R, D)
+                d_c1 = colsum(dZ, D, R, D, weight=rs)
+                dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
+                d_W2 = torch.empty((D, D), **f32)       # dWc W1^T + d_c1 b1^T
+                gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=1)
+                d_W1 = torch.empty((D, D), **f32)       # W2^T dWc
+                gemm_raw(_ptr(W2), D, 0, _ptr(dWc), D, 0, _ptr(d_W1), D, D, D, D, splits=1)
+                d_b1 = torch.empty((D,), **f32)         # W2^T d_c1
+                gemm_raw(_ptr(W2), D, 0, _ptr(d_c1), 1, 0, _ptr(d_b1), 1, D, 1, D, splits=1)
+                fork.keep.extend((dWc, d_c1))
             dG = pr.linear_dx(dZ, D, Wc, R)
             dGin_i = pr.empty((R, D), dev)
             call("fira_gcn_aggregate", _ptr(et.rowptr), _ptr(et.col), _ptr(et.val), _ptr(dG), _ptr(dRes),
                  _ptr(dGin_i), B, n_code, n_sub, n_ast, D, pr.code, st)
-            d_W2 = torch.empty((D, D), **f32)       # dWc W1^T + d_c1 b1^T
-            gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=1)
-            d_W1 = torch.empty((D, D), **f32)       # W2^T dWc
-            gemm_raw(_ptr(W2), D, 0, _ptr(dWc), D, 0, _ptr(d_W1), D, D, D, D, splits=1)
-            d_b1 = torch.empty((D,), **f32)         # W2^T d_c1
-            gemm_raw(_ptr(W2), D, 0, _ptr(d_c1), 1, 0, _ptr(d_b1), 1, D, 1, D, splits=1)
             # ---- Combination backward (rows < Mc of dGin_i are d(comb output))
             dXc_n = pr.empty((Mc, D), dev)
             dZc, _, d_clw, d_clb = pr.ln_bwd(dGin_i, dGin_i, Mc, Zc, Xc, st_c, clw, Mc, p_comb, seed, sid + 1,
                                              d_resid=dXc_n)
-            d_bo = colsum(dZc, D, Mc, D)
-            d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D)
+            with fork(dZc, Cd):
+                d_bo = colsum(dZc, D, Mc, D)
+                d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D)
             dCd = pr.linear_dx(dZc, D, Wo, Mc)
             dQK = pr.empty((Mc, 2 * D), dev)
             dVtab = torch.zeros((4, D), **f32)
             call("fira_comb_gate_bwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(dCd), _ptr(dQK), _ptr(dVtab),
                  Mc, D, D // heads, float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
-            d_bqk = colsum(dQK, 2 * D, Mc, 2 * D)
-            d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D)
+            with fork(dQK, Xc, dVtab, mark_emb, Wv, d_mark_emb):
+                d_bqk = colsum(dQK, 2 * D, Mc, 2 * D)
+                d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D)
+                d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D)
+                d_bv = colsum(dVtab, D, 4, D)
+                linear_dx(dVtab, D, Wv, 4, out=d_mark_emb, accumulate=True)
             pr.linear_dx(dQK, 2 * D, Wqk, Mc, out=dXc_n, accumulate=True)
-            d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D)
-            d_bv = colsum(dVtab, D, 4, D)
-            linear_dx(dVtab, D, Wv, 4, out=d_mark_emb, accumulate=True)
             grads[i * 16:(i + 1) * 16] = [d_Wqk[:D], d_bqk[:D], d_Wqk[D:], d_bqk[D:], d_Wv, d_bv, d_Wo, d_bo,
                                           d_clw, d_clb, d_W1, d_b1, d_W2, d_b2, d_glw, d_glb]
             dXc, dGin = dXc_n, dGin_i
@@ -340,6 +378,7 @@ class EncoderFn(torch.autograd.Function):
         d_ast = torch.zeros_like(ast_emb)
         call("fira_embed_nodes_bwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(dXc), _ptr(dGin),
              _ptr(d_emb), _ptr(d_ast), B, n_code, n_sub, n_ast, D, pr.code, st)
+        fork.join()
         d_mark_emb[0].zero_()     # padding_idx=0 (gnn_transformer.py:39)
         return (None, None, None, None, None, None, None, d_emb, d_ast, d_mark_emb, *grads)
 
@@ -429,6 +468,7 @@ class DecoderFn(torch.autograd.Function):
         dKV = pr.empty((Ms, ldkv), dev)
         grads = [None] * len(lp)
         F = 4 * D
+        fork = Fork(dev)
         for i in reversed(range(L)):
             (sWq, sbq, sWk, sbk, sWv, sbv, sWo, sbo, slw, slb,
              cWq, cbq, cWk, cbk, cWv, cbv, cWo, cbo, clw, clb,
@@ -437,36 +477,42 @@ class DecoderFn(torch.autograd.Function):
             sid = cfg["stream_base"] + 64 + i * 8
             # ---- FFN
             dZ3, dX2, d_flw, d_flb = pr.ln_bwd(dX, dX, Mt, Z3, X2, ls3, flw, Mt, p, seed, sid + 2)
-            d_fb2 = colsum(dZ3, D, Mt, D)
-            d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F)
+            with fork(dZ3, Hh):
+                d_fb2 = colsum(dZ3, D, Mt, D)
+                d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F)
             dHh = pr.linear_dx(dZ3, D, fW2, Mt)                           # [Mt, 1024]
             call("fira_relu_bwd", _ptr(Hh), _ptr(dHh), Mt * F, pr.code, st)
-            d_fb1 = colsum(dHh, F, Mt, F)
-            d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D)
+            with fork(dHh, X2):
+                d_fb1 = colsum(dHh, F, Mt, F)
+                d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D)
             pr.linear_dx(dHh, F, fW1, Mt, out=dX2, accumulate=True)
             # ---- cross-attention
             dZ2, dX1, d_clw, d_clb = pr.ln_bwd(dX2, dX2, Mt, Z2, X1, ls2, clw, Mt, p, seed, sid + 1)
-            d_cbo = colsum(dZ2, D, Mt, D)
-            d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D)
+            with fork(dZ2, ctx2):
+                d_cbo = colsum(dZ2, D, Mt, D)
+                d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D)
             dctx2 = pr.linear_dx(dZ2, D, cWo, Mt)
             dQ = pr.empty((Mt, D), dev)
             call("fira_attn_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
                  _ptr(mem_mask), 0, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
                  _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
-            d_cbq = colsum(dQ, D, Mt, D)
-            d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D)
+            with fork(dQ, X1):
+                d_cbq = colsum(dQ, D, Mt, D)
+                d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D)
             pr.linear_dx(dQ, D, cWq, Mt, out=dX1, accumulate=True)
             # ---- self-attention
             dZ1, dX0, d_slw, d_slb = pr.ln_bwd(dX1, dX1, Mt, Z1, X, ls1, slw, Mt, p, seed, sid + 0)
-            d_sbo = colsum(dZ1, D, Mt, D)
-            d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D)
+            with fork(dZ1, ctx1):
+                d_sbo = colsum(dZ1, D, Mt, D)
+                d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D)
             dctx1 = pr.linear_dx(dZ1, D, sWo, Mt)
             dQKV = pr.empty((Mt, 3 * D), dev)
             call("fira_attn_bwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
                  _ptr(ctx1), _ptr(dctx1), D, _ptr(st1), _ptr(dQKV), 3 * D, _ptr(dQKV, D), 3 * D, _ptr(dQKV, 2 * D), 3 * D,
                  B, H, T, T, D // H, pr.code, st)
-            d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D)
-            d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D)
+            with fork(dQKV, X):
+                d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D)
+                d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D)
             pr.linear_dx(dQKV, 3 * D, Wqkv, Mt, out=dX0, accumulate=True)
             grads[i * 26:(i + 1) * 26] = [
                 d_Wqkv[:D], d_bqkv[:D], d_Wqkv[D:2 * D], d_bqkv[D:2 * D], d_Wqkv[2 * D:], d_bqkv[2 * D:],
@@ -477,8 +523,9 @@ class DecoderFn(torch.autograd.Function):
             ctx.saved[i] = None
         # hoisted K/V projections of the memory: one weight-grad GEMM, one input-grad GEMM
         mem2 = memory.view(Ms, D)
-        d_bkv = colsum(dKV, ldkv, Ms, ldkv)
-        d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D)
+        with fork(dKV, mem2):
+            d_bkv = colsum(dKV, ldkv, Ms, ldkv)
+            d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D)
         d_mem = pr.linear_dx(dKV, ldkv, Wkv, Ms).view(B, S, D).to(mem_dtype)
         for i in range(L):
             o = i * 2 * D
@@ -486,6 +533,7 @@ class DecoderFn(torch.autograd.Function):
             grads[i * 26 + 14], grads[i * 26 + 15] = d_Wkv[o + D:o + 2 * D], d_bkv[o + D:o + 2 * D]
         d_emb = torch.zeros_like(dec_emb)
         call("fira_embed_rows_bwd", _ptr(tar), _ptr(dX), _ptr(d_emb), Mt, D, pr.code, st)
+        fork.join()
         return (None, None, d_mem, None, None, None, d_emb, *grads)
 
 
@@ -564,22 +612,25 @@ class HeadFn(torch.autograd.Function):
         d_bres = torch.zeros((1,), **f32)
         call("fira_copy_scores_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(d_src),
              _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
-        d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D)
+        fork = Fork(dev)
+        with fork(d_src, memory2, dlogits, dec2, dgl, dec32, d_tgt):
+            d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D)
+            d_bout = colsum(dlogits, ldl, Mt, V)
+            d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D)
+            d_bp = colsum(dgl, 2, Mt, 2)
+            d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D)
+            d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D)
         d_mem = pr.linear_dx(d_src, D, Ws, Ms)
         # vocabulary projection (the big one), gate and target projection; d_dec accumulates in fp32
-        d_bout = colsum(dlogits, ldl, Mt, V)
-        d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D)
         if pr.bf16:
             d_dec = torch.empty((Mt, D), **f32)
             gemm_tc(dlogits, ldl, 1, pr.w(Wout), D, 0, d_dec, D, Mt, D, V,
                     splits=_tc_splits(_ceil(Mt, 128), _ceil(V, 64)))
         else:
             d_dec = linear_dx(dlogits, ldl, Wout, Mt)
-        d_bp = colsum(dgl, 2, Mt, 2)
-        d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D)
         linear_dx(dgl, 2, Wp, Mt, out=d_dec, accumulate=True)
-        d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D)
         linear_dx(d_tgt, D, Wt, Mt, out=d_dec, accumulate=True)
+        fork.join()
         return (None, None, d_mem.view(B, S, D).to(mem_dt), d_dec.view(B, T, D).to(dec_dt), None, None, d_Wout, d_bout,
                 d_Ws, d_Wt, d_wres, d_bres, d_Wp, d_bp)
 
