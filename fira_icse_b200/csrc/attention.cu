@@ -82,6 +82,10 @@ __device__ __forceinline__ void compact_keys(const unsigned char* km, int Lk, in
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// Keys are consumed in chunks of KC with a running (max, sum, output) per query row (online softmax), so the
+// shared-memory footprint is ~48 KB whatever Lk is: 4 CTAs per SM instead of 1 for Lk = 370.
+constexpr int PAIRS_MAX = (LQ_MAX / 2 + NWARPS - 1) / NWARPS;      // query-row pairs per warp (2)
+
 template <typename T>
 __global__ void __launch_bounds__(NTHR) attn_fwd_kernel(AttnArgs a, T* __restrict__ ctx, long ldo,
                                                         float* __restrict__ stats /* [B,H,Lq,2] */) {
@@ -89,56 +93,79 @@ __global__ void __launch_bounds__(NTHR) attn_fwd_kernel(AttnArgs a, T* __restric
   __shared__ int nv_s, filled_s;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* Ks = smem;                          // [Lk][KPAD]   (first nv rows used)
-  float* Vs = Ks + a.Lk * KPAD;              // [Lk][KPAD]
-  float* Qs = Vs + a.Lk * KPAD;              // [Lq][KPAD]
-  float* Ps = Qs + a.Lq * KPAD;              // [NWARPS][2][Lk]
-  int* kidx = reinterpret_cast<int*>(Ps + NWARPS * 2 * a.Lk);   // [Lk]
-  compact_keys(a.key_mask + (long)b * a.Lk, a.Lk, a.causal, kidx, &nv_s, &filled_s);
+  float* Ks = smem;                          // [KC][KPAD]
+  float* Vs = Ks + KC * KPAD;                // [KC][KPAD]
+  float* Qs = Vs + KC * KPAD;                // [Lq][KPAD]
+  float* Ps = Qs + a.Lq * KPAD;              // [NWARPS][2][KC]
+  int* kidx = reinterpret_cast<int*>(Ps + NWARPS * 2 * KC);   // [Lk]
   const unsigned char* km = a.key_mask + (long)b * a.Lk;
+  compact_keys(km, a.Lk, a.causal, kidx, &nv_s, &filled_s);
   const int nv = nv_s;
   const bool filled = filled_s != 0;
-  load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, 0, nv);
-  load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, 0, nv);
   load_rows(Qs, (const T*)a.q + (long)b * a.Lq * a.ldq + h * DH, a.ldq, nullptr, 0, a.Lq);
-  __syncthreads();
-  float* P0 = Ps + (warp * 2 + 0) * a.Lk;
-  float* P1 = Ps + (warp * 2 + 1) * a.Lk;
-  for (int t0 = warp * 2; t0 < a.Lq; t0 += NWARPS * 2) {
-    const int t1 = min(t0 + 1, a.Lq - 1);                // odd Lq: row duplicated, second result dropped
-    float q0[DH], q1[DH];
+  float* P0 = Ps + (warp * 2 + 0) * KC;
+  float* P1 = Ps + (warp * 2 + 1) * KC;
+  float m0[PAIRS_MAX], m1[PAIRS_MAX], l0[PAIRS_MAX], l1[PAIRS_MAX], o0[PAIRS_MAX], o1[PAIRS_MAX];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) { q0[d] = Qs[t0 * KPAD + d]; q1[d] = Qs[t1 * KPAD + d]; }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-    for (int j = lane; j < nv; j += 32) {
-      float s0 = 0.f, s1 = 0.f;
+  for (int i = 0; i < PAIRS_MAX; ++i) { m0[i] = m1[i] = -INFINITY; l0[i] = l1[i] = 0.f; o0[i] = o1[i] = 0.f; }
+
+  for (int c0 = 0; c0 < nv; c0 += KC) {
+    const int nc = min(KC, nv - c0);
+    __syncthreads();                                       // previous chunk consumed; Qs visible
+    load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, c0, nc);
+    load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, c0, nc);
+    __syncthreads();
 #pragma unroll
-      for (int d = 0; d < DH; ++d) { const float kd = Ks[j * KPAD + d]; s0 = fmaf(q0[d], kd, s0); s1 = fmaf(q1[d], kd, s1); }
-      const int ko = kidx[j];
-      const bool pad = filled || (a.causal && km[ko] == 0);
-      s0 = (pad || (a.causal && ko > t0)) ? kMaskFill : s0 * a.scale;
-      s1 = (pad || (a.causal && ko > t1)) ? kMaskFill : s1 * a.scale;
-      P0[j] = s0; P1[j] = s1;
-      mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+    for (int i = 0; i < PAIRS_MAX; ++i) {
+      const int t0 = (warp + i * NWARPS) * 2;
+      if (t0 < a.Lq) {
+        const int t1 = min(t0 + 1, a.Lq - 1);              // odd Lq: row duplicated, second result dropped
+        float q0[DH], q1[DH];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { q0[d] = Qs[t0 * KPAD + d]; q1[d] = Qs[t1 * KPAD + d]; }
+        float cm0 = -INFINITY, cm1 = -INFINITY;
+        for (int j = lane; j < nc; j += 32) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) { const float kd = Ks[j * KPAD + d]; s0 = fmaf(q0[d], kd, s0); s1 = fmaf(q1[d], kd, s1); }
+          const int ko = kidx[c0 + j];
+          const bool pad = filled || (a.causal && km[ko] == 0);
+          s0 = (pad || (a.causal && ko > t0)) ? kMaskFill : s0 * a.scale;
+          s1 = (pad || (a.causal && ko > t1)) ? kMaskFill : s1 * a.scale;
+          P0[j] = s0; P1[j] = s1;
+          cm0 = fmaxf(cm0, s0); cm1 = fmaxf(cm1, s1);
+        }
+        const float nm0 = fmaxf(m0[i], warp_max(cm0)), nm1 = fmaxf(m1[i], warp_max(cm1));
+        const float r0 = expf(m0[i] - nm0), r1 = expf(m1[i] - nm1);     // exp(-inf) = 0 on the first chunk
+        float sum0 = 0.f, sum1 = 0.f;
+        for (int j = lane; j < nc; j += 32) {
+          const float e0 = expf(P0[j] - nm0), e1 = expf(P1[j] - nm1);
+          P0[j] = e0; P1[j] = e1; sum0 += e0; sum1 += e1;
+        }
+        l0[i] = l0[i] * r0 + warp_sum(sum0);
+        l1[i] = l1[i] * r1 + warp_sum(sum1);
+        m0[i] = nm0; m1[i] = nm1;
+        __syncwarp();
+        float a0 = o0[i] * r0, a1 = o1[i] * r1;
+        for (int j = 0; j < nc; ++j) { const float vv = Vs[j * KPAD + lane]; a0 = fmaf(P0[j], vv, a0); a1 = fmaf(P1[j], vv, a1); }
+        o0[i] = a0; o1[i] = a1;
+        __syncwarp();
+      }
     }
-    mx0 = warp_max(mx0); mx1 = warp_max(mx1);
-    float sum0 = 0.f, sum1 = 0.f;
-    for (int j = lane; j < nv; j += 32) {
-      const float e0 = expf(P0[j] - mx0), e1 = expf(P1[j] - mx1);
-      P0[j] = e0; P1[j] = e1; sum0 += e0; sum1 += e1;
+  }
+#pragma unroll
+  for (int i = 0; i < PAIRS_MAX; ++i) {
+    const int t0 = (warp + i * NWARPS) * 2;
+    if (t0 < a.Lq) {
+      const int t1 = min(t0 + 1, a.Lq - 1);
+      Act<T>::st(ctx + ((long)b * a.Lq + t0) * ldo + h * DH + lane, o0[i] / l0[i]);
+      if (t1 != t0) Act<T>::st(ctx + ((long)b * a.Lq + t1) * ldo + h * DH + lane, o1[i] / l1[i]);
+      if (lane == 0 && stats) {
+        float* st = stats + (((long)b * a.H + h) * a.Lq + t0) * 2;
+        st[0] = m0[i]; st[1] = l0[i];
+        if (t1 != t0) { st[2] = m1[i]; st[3] = l1[i]; }
+      }
     }
-    sum0 = warp_sum(sum0); sum1 = warp_sum(sum1);
-    __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < nv; ++j) { const float vv = Vs[j * KPAD + lane]; o0 = fmaf(P0[j], vv, o0); o1 = fmaf(P1[j], vv, o1); }
-    Act<T>::st(ctx + ((long)b * a.Lq + t0) * ldo + h * DH + lane, o0 / sum0);
-    if (t1 != t0) Act<T>::st(ctx + ((long)b * a.Lq + t1) * ldo + h * DH + lane, o1 / sum1);
-    if (lane == 0 && stats) {
-      float* st = stats + (((long)b * a.H + h) * a.Lq + t0) * 2;
-      st[0] = mx0; st[1] = sum0;
-      if (t1 != t0) { st[2] = mx1; st[3] = sum1; }
-    }
-    __syncwarp();
   }
 }
 
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
 }
 
 size_t fwd_smem(int Lq, int Lk) {
-  return sizeof(float) * ((size_t)2 * Lk * KPAD + (size_t)Lq * KPAD + (size_t)NWARPS * 2 * Lk) + sizeof(int) * (size_t)Lk;
+  return sizeof(float) * ((size_t)2 * KC * KPAD + (size_t)Lq * KPAD + (size_t)NWARPS * 2 * KC) + sizeof(int) * (size_t)Lk;
 }
 size_t bwd_smem(int Lq, int Lk) {
   return sizeof(float) * ((size_t)2 * KC * KPAD + (size_t)2 * Lq * KPAD + (size_t)2 * Lq * (KC + 1)) +
@@ -283,7 +310,7 @@ int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* 
                   const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
                   int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_fwd: d_head %d != 32", d_head);
-  FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, FIRA_ERR_SHAPE, "attn_fwd: shape");
+  FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lq <= LQ_MAX, FIRA_ERR_SHAPE, "attn_fwd: shape (Lq <= 32)");
   FIRA_CHECK_ARG(!causal || Lq == Lk, FIRA_ERR_SHAPE, "attn_fwd: causal needs Lq == Lk");
   FIRA_CHECK_ARG(dtype == FIRA_F32 || dtype == FIRA_BF16, FIRA_ERR_DTYPE, "attn_fwd: dtype %d", dtype);
   int rc;

@@ -19,7 +19,11 @@ template <typename T>
 __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restrict__ src, const T* __restrict__ tgt,
                                                               const float* __restrict__ w_res,
                                                               const float* __restrict__ b_res_p,
+                                                              const unsigned char* __restrict__ src_mask,
+                                                              const unsigned char* __restrict__ row_mask,
                                                               float* __restrict__ sc, int B, int Tn, int S) {
+  // src_mask / row_mask (optional): padded source positions are overwritten with -1e9 by the mixture kernel
+  // (Model.py:61) and target rows without a label never reach the loss -- both are skipped (score 0 written).
   const float b_res = *b_res_p;
   __shared__ __align__(16) float tg[TMAX][D];
   __shared__ __align__(16) float wr[D];
@@ -33,9 +37,17 @@ __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restric
   const int rows_per_cta = 32;
   const int s_end = min(S, (int)(blockIdx.x + 1) * rows_per_cta);
   for (int s = blockIdx.x * rows_per_cta + warp; s < s_end; s += 8) {
+    if (src_mask && src_mask[(long)b * S + s] == 0) {
+      for (int t = lane; t < Tn; t += 32) sc[((long)b * Tn + t) * S + s] = 0.f;
+      continue;
+    }
     float x[8];
     Act<T>::load8(src + ((long)b * S + s) * D + lane * 8, x);
     for (int t = 0; t < Tn; ++t) {
+      if (row_mask && row_mask[(long)b * Tn + t] == 0) {          // warp-uniform
+        if (lane == 0) sc[((long)b * Tn + t) * S + s] = 0.f;
+        continue;
+      }
       float y[8];
       Act<float>::load8(&tg[t][lane * 8], y);
       float acc = 0.f;
@@ -168,9 +180,15 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ log
   const float* srow = sc + row * S;
   const unsigned char* mrow = mem_mask + (long)b * S;
 
-  // pass 1: vocab max / sum-exp (online), copy max / sum-exp with the -1e9 fill (Model.py:61)
+  // pass 1: vocab max / sum-exp (online), copy max / sum-exp with the -1e9 fill (Model.py:61).
+  // Training (no argmax wanted): a row's loss only needs the softmax its label lives in, so rows whose label is
+  // padding or a copy label skip the 24,650-wide pass (and copy-label rows are the only ones that need `sc`).
+  const int lab_row = label[row];
+  const bool need_vocab = argmax_out != nullptr || (lab_row != 0 && lab_row < V);
   MaxSum v{-INFINITY, 0.f};
-  for (int j = threadIdx.x; j < V; j += blockDim.x) { MaxSum u{Act<T>::ld(lrow + j), 1.f}; v = ms_merge(v, u); }
+  if (need_vocab)
+    for (int j = threadIdx.x; j < V; j += blockDim.x) { MaxSum u{Act<T>::ld(lrow + j), 1.f}; v = ms_merge(v, u); }
+  else if (threadIdx.x == 0) v = MaxSum{0.f, 1.f};
   v = ms_warp(v);
   if (lane == 0) sh_ms[warp] = v;
   __syncthreads();
@@ -289,14 +307,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ log
 
 extern "C" {
 
-int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res, float* scores,
+int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
+                         const unsigned char* src_mask, const unsigned char* row_mask, float* scores,
                          int B, int T_len, int S, int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "copy_scores_fwd: dim %d != 256", dim);
   FIRA_CHECK_ARG(T_len > 0 && T_len <= TMAX, FIRA_ERR_SHAPE, "copy_scores_fwd: T_len %d > %d", T_len, TMAX);
   if (B == 0 || S == 0) return FIRA_OK;
   dim3 grid((S + 31) / 32, B);
   DISPATCH_T(dtype, copy_scores_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const T*)src_proj, (const T*)tgt_proj, w_res, b_res, scores, B, T_len, S);)
+      (const T*)src_proj, (const T*)tgt_proj, w_res, b_res, src_mask, row_mask, scores, B, T_len, S);)
   FIRA_CHECK_LAUNCH("fira_copy_scores_fwd");
   return FIRA_OK;
 }

@@ -542,12 +542,12 @@ def _ld_logits(V):
     return (V + 63) // 64 * 64
 
 
-def copy_scores_fwd(pr, memory2, dec2, Ws, Wt, wres, bres, B, T, S):
+def copy_scores_fwd(pr, memory2, dec2, Ws, Wt, wres, bres, B, T, S, src_mask=None, row_mask=None):
     src = pr.linear(memory2, Ws)                  # [B*S, 256]
     tgt = pr.linear(dec2, Wt)                     # [B*T, 256]
     sc = torch.empty((B, T, S), dtype=torch.float32, device=dec2.device)
-    call("fira_copy_scores_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(sc), B, T, S, D, pr.code,
-         _stream())
+    call("fira_copy_scores_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(src_mask), _ptr(row_mask),
+         _ptr(sc), B, T, S, D, pr.code, _stream())
     return src, tgt, sc
 
 
@@ -573,7 +573,11 @@ class HeadFn(torch.autograd.Function):
         ldl = _ld_logits(V)
         logits = pr.empty((Mt, ldl), dev)
         pr.linear(dec2, Wout, bout, out=logits, ld_out=ldl)
-        src, tgt, sc = copy_scores_fwd(pr, memory2, dec2, Ws, Wt, Wres, bres, B, T, S)
+        # training only needs pointer scores of real source positions at target rows whose label is a COPY
+        # label (vocabulary-label rows take their loss from the vocabulary softmax alone, Model.py:64-81)
+        row_mask = None if want_argmax else (label >= V).to(torch.uint8)
+        src, tgt, sc = copy_scores_fwd(pr, memory2, dec2, Ws, Wt, Wres, bres, B, T, S, src_mask=mem_mask,
+                                       row_mask=row_mask)
         gl = linear(dec32, Wp, bp)                # fp32 [Mt, 2]
         stats = torch.empty((Mt, 8), **f32)
         nll = torch.empty((Mt,), **f32)

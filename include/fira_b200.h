@@ -127,8 +127,10 @@ int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* 
                   const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
                   int Lq, int Lk, int d_head, int dtype, void* stream);
 
-/* ---- CopyNet scores (Model.py:17-18): sc[b,t,s] = b_res + w_res . tanh(src[b,s] + tgt[b,t]). */
-int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res, float* scores,
+/* ---- CopyNet scores (Model.py:17-18): sc[b,t,s] = b_res + w_res . tanh(src[b,s] + tgt[b,t]).
+ *      src_mask [B,S] / row_mask [B*T] (optional, 1 = compute): positions the caller will mask anyway. */
+int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
+                         const unsigned char* src_mask, const unsigned char* row_mask, float* scores,
                          int B, int T_len, int S, int dim, int dtype, void* stream);
 int fira_copy_scores_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
                          const unsigned char* row_active, void* d_src_proj, float* d_tgt_proj, float* d_w_res,

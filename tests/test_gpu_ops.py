@@ -320,11 +320,20 @@ def test_copy_scores_fwd_bwd():
     w, b = rnd(1, 256, seed=3, scale=0.2), rnd(1, seed=4)
     sc = torch.empty(B, T, S, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.call("fira_copy_scores_fwd", src.data_ptr(), tgt.data_ptr(), w.data_ptr(), b.data_ptr(), sc.data_ptr(), B, T,
-              S, 256, 0, st)
+    _lib.call("fira_copy_scores_fwd", src.data_ptr(), tgt.data_ptr(), w.data_ptr(), b.data_ptr(), None, None,
+              sc.data_ptr(), B, T, S, 256, 0, st)
     sd_, td_, wd, bd = (t.double().requires_grad_(True) for t in (src, tgt, w, b))
     ref = (torch.tanh(sd_.view(B, 1, S, 256) + td_.view(B, T, 1, 256)) * wd.view(1, 1, 1, 256)).sum(-1) + bd
     close(sc, ref, rtol=1e-5, atol=1e-5)
+    # optional masks: skipped positions are written as 0, the others are unchanged
+    gmask = torch.Generator().manual_seed(11)
+    sm = (torch.rand(B, S, generator=gmask) > 0.5).to(torch.uint8).to(DEV)
+    rm = (torch.rand(B * T, generator=gmask) > 0.5).to(torch.uint8).to(DEV)
+    sc2 = torch.full_like(sc, 7.0)
+    _lib.call("fira_copy_scores_fwd", src.data_ptr(), tgt.data_ptr(), w.data_ptr(), b.data_ptr(), sm.data_ptr(),
+              rm.data_ptr(), sc2.data_ptr(), B, T, S, 256, 0, st)
+    keep = rm.view(B, T, 1).bool() & sm.view(B, 1, S).bool()
+    assert torch.equal(sc2[keep], sc[keep]) and (sc2[~keep] == 0).all()
     gm = torch.Generator().manual_seed(5)
     active = (torch.rand(B * T, generator=gm) > 0.7).to(torch.uint8).to(DEV)
     dsc = rnd(B, T, S, seed=6) * active.view(B, T, 1)
