@@ -9,7 +9,7 @@
 // keeps the reference's behaviour: uniform P over all keys, no gradient to the scores.
 // Each warp handles two query rows at a time so every K / V shared-memory read feeds two rows.
 // Forward saves (row max, row sum); backward recomputes P from them, gets delta = rowsum(P * dP) as
-// dO . O (so keys can be processed in chunks of 128 with a small shared-memory footprint, 3 CTAs/SM)
+// dO . O (so keys can be processed in chunks of 64 with a small shared-memory footprint, 5 CTAs/SM)
 // and writes zero gradients for the masked keys.
 #include "common.cuh"
 #include "fira_b200.h"
@@ -20,7 +20,8 @@ constexpr int DH = 32;           // head dim (256 / 8)
 constexpr int KPAD = DH + 1;     // conflict-free column reads of K/V tiles
 constexpr int NWARPS = 8;
 constexpr int NTHR = NWARPS * 32;
-constexpr int KC = 128;          // keys per backward chunk
+constexpr int KC = 128;          // keys per forward chunk
+constexpr int KCB = 64;          // keys per backward chunk (42 KB shared memory -> 5 CTAs per SM)
 constexpr int LQ_MAX = 32;       // tar_len 30 (run_model.py:32)
 
 struct AttnArgs {
@@ -181,10 +182,10 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
   __shared__ float delta_s[LQ_MAX], mx_s[LQ_MAX], inv_s[LQ_MAX];
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int PP = KC + 1;
-  float* Ks = smem;                          // [KC][KPAD]
-  float* Vs = Ks + KC * KPAD;                // [KC][KPAD]
-  float* Qs = Vs + KC * KPAD;                // [Lq][KPAD]
+  constexpr int PP = KCB + 1;
+  float* Ks = smem;                          // [KCB][KPAD]
+  float* Vs = Ks + KCB * KPAD;                // [KCB][KPAD]
+  float* Qs = Vs + KCB * KPAD;                // [Lq][KPAD]
   float* Os = Qs + a.Lq * KPAD;              // [Lq][KPAD]  dO
   float* Pm = Os + a.Lq * KPAD;              // [Lq][PP]    P
   float* Sm = Pm + a.Lq * PP;                // [Lq][PP]    dS
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
 #pragma unroll
   for (int i = 0; i < (LQ_MAX + NWARPS - 1) / NWARPS; ++i) dqa[i] = 0.f;
 
-  for (int c0 = 0; c0 < nv; c0 += KC) {
-    const int nc = min(KC, nv - c0);
+  for (int c0 = 0; c0 < nv; c0 += KCB) {
+    const int nc = min(KCB, nv - c0);
     __syncthreads();                                     // previous chunk fully consumed (and Qs loaded)
     load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, c0, nc);
     load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, c0, nc);
@@ -276,7 +277,7 @@ size_t fwd_smem(int Lq, int Lk) {
   return sizeof(float) * ((size_t)2 * KC * KPAD + (size_t)Lq * KPAD + (size_t)NWARPS * 2 * KC) + sizeof(int) * (size_t)Lk;
 }
 size_t bwd_smem(int Lq, int Lk) {
-  return sizeof(float) * ((size_t)2 * KC * KPAD + (size_t)2 * Lq * KPAD + (size_t)2 * Lq * (KC + 1)) +
+  return sizeof(float) * ((size_t)2 * KCB * KPAD + (size_t)2 * Lq * KPAD + (size_t)2 * Lq * (KCB + 1)) +
          sizeof(int) * (size_t)Lk;
 }
 
