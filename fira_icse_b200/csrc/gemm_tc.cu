@@ -1,6 +1,6 @@
 // bf16 tensor-core GEMM for the throughput path: tcgen05.mma (UMMA, SASS UTCHMMA) with the fp32
 // accumulator in TMEM, operands staged in shared memory by TMA (cp.async.bulk.tensor, SASS UTMALDG)
-// through a 4-stage mbarrier ring, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+// through a 2-3 stage mbarrier ring (two CTAs per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> bias / rank-1 / relu ->
 // global).  One 128 x BN output tile per CTA, cta_group::1.
 //
@@ -23,7 +23,6 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 192; // 6 warps
 
 struct TcParams {
@@ -84,8 +83,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 //   K-major operand  : [rows][64 k]          rows x 128 B, 8-row groups 1024 B apart (SBO = 1024)
 //   MN-major operand : [mn/64][64 k][64 mn]  each 64-mn panel is 64 k-rows x 128 B = 8 KB (LBO = 8192 between
 //                      panels, SBO = 1024 between 8-k groups); one TMA box per panel.
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -165,122 +164,127 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue: TMEM -> registers -> smem (lane = row) -> global (lane = column) =====
     // tcgen05.ld hands every lane ONE accumulator row; storing that straight to global makes each warp
     // store touch 32 different rows (32 sectors per instruction: measured ~30 us per tile, round 1).  So the
-    // warp first parks its 32 x BN fp32 block in the (now idle) pipeline stages with a +16 B row pitch
-    // (conflict-free float4 writes), then streams it out row by row: 32 lanes x 8 consecutive columns =
-    // 512 B (bf16) / 1 KB (fp32) contiguous per store; bias / rank-1 / relu / accumulate / split-K atomics
-    // are applied on the way out with per-lane column constants.
+    // warp parks a 32 x HB fp32 block in the (now idle) pipeline stages with a +16 B row pitch
+    // (conflict-free float4 writes), then streams it out with lanes across the columns of a row:
+    // contiguous 256-512 B (bf16) / 512 B-1 KB (fp32) per store; bias / rank-1 / relu / accumulate /
+    // split-K atomics are applied on the way out with per-lane column constants.  HB = 128 columns at a
+    // time keeps the staging area inside two pipeline stages, so two CTAs fit per SM and one CTA's
+    // epilogue overlaps the other's TMA/MMA phase.
     const int quarter = warp & 3;                   // TMEM lanes [32*quarter, +32) are this warp's
-    constexpr int PITCH = BN + 4;                   // floats
+    constexpr int HB = BN < 128 ? BN : 128;         // columns staged per pass
+    constexpr int PITCH = HB + 4;                   // floats
+    constexpr int LPR = HB / 8;                     // lanes per row on the way out (8 columns per lane)
+    constexpr int RPI = 32 / LPR;                   // rows per store iteration
     float* stg = reinterpret_cast<float*>(smem_dyn + (base - smem_addr(smem_dyn))) + (size_t)quarter * 32 * PITCH;
     if (nkb > 0) {
       mbar_wait(smem_addr(&tmem_full_bar), 0);
       tc_fence_after();
     }
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      if (nkb > 0) {
-        const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      float* dst = stg + (size_t)lane * PITCH + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    }
-    __syncwarp();
     const bool first = blockIdx.z == 0;
     const int mrow0 = m0 + quarter * 32;
-    if (p.splits > 1) {
-      // split-K partials: lane <-> consecutive columns, so every RED.ADD of a warp covers one 128-B line
-      for (int rr = 0; rr < 32; ++rr) {
-        const int m = mrow0 + rr;
-        if (m >= p.M) break;
-        const float rsm = (p.rs && first) ? p.rs[m] : 0.f;
-        float* crow = (float*)p.C + (long)m * p.ldc;
+#pragma unroll 1
+    for (int hb = 0; hb < BN; hb += HB) {
+#pragma unroll 1
+      for (int c = 0; c < HB / 32; ++c) {
+        uint32_t r[32];
+        if (nkb > 0) {
+          const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(hb + c * 32);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
 #pragma unroll
-        for (int jg = 0; jg < BN / 32; ++jg) {
-          const int n = n0 + jg * 32 + lane;
-          if (n < p.N) {
-            float x = stg[(size_t)rr * PITCH + jg * 32 + lane];
-            if (first) {
-              if (p.bias) x += p.bias[n];
-              if (p.rs) x = fmaf(rsm, p.rc[n], x);
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        float* dst = stg + (size_t)lane * PITCH + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+      __syncwarp();
+      if (p.splits > 1) {
+        // split-K partials: lane <-> consecutive columns, so every RED.ADD of a warp covers one 128-B line
+        for (int rr = 0; rr < 32; ++rr) {
+          const int m = mrow0 + rr;
+          if (m >= p.M) break;
+          const float rsm = (p.rs && first) ? p.rs[m] : 0.f;
+          float* crow = (float*)p.C + (long)m * p.ldc;
+#pragma unroll
+          for (int jg = 0; jg < HB / 32; ++jg) {
+            const int n = n0 + hb + jg * 32 + lane;
+            if (n < p.N) {
+              float x = stg[(size_t)rr * PITCH + jg * 32 + lane];
+              if (first) {
+                if (p.bias) x += p.bias[n];
+                if (p.rs) x = fmaf(rsm, p.rc[n], x);
+              }
+              atomicAdd(crow + n, x);
             }
-            atomicAdd(crow + n, x);
           }
         }
-      }
-    }
-    const int col = lane * 8;
-    if (p.splits <= 1 && col < BN) {
-      const int n = n0 + col;
-      float bv[8], rcv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        bv[j] = (p.bias && first && n + j < p.N) ? p.bias[n + j] : 0.f;
-        rcv[j] = (p.rs && first && n + j < p.N) ? p.rc[n + j] : 0.f;
-      }
-      const bool full = n + 7 < p.N;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int m = mrow0 + rr;
-        if (m >= p.M) break;
-        const float rsm = (p.rs && first) ? p.rs[m] : 0.f;          // same address in every lane: one broadcast load
-        float v[8];
-        const float4 x0 = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + col);
-        const float4 x1 = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + col + 4);
-        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      } else {
+        const int col = (lane % LPR) * 8;
+        const int n = n0 + hb + col;
+        float bv[8], rcv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v[j] = fmaf(rsm, rcv[j], v[j] + bv[j]);
-          if (p.relu) v[j] = fmaxf(v[j], 0.f);
+          bv[j] = (p.bias && first && n + j < p.N) ? p.bias[n + j] : 0.f;
+          rcv[j] = (p.rs && first && n + j < p.N) ? p.rc[n + j] : 0.f;
         }
-        if (p.splits > 1) {
-          float* cp = (float*)p.C + (long)m * p.ldc + n;
+        const bool full = n + 7 < p.N;
+        for (int it = 0; it < 32 / RPI; ++it) {
+          const int rr = it * RPI + lane / LPR;
+          const int m = mrow0 + rr;
+          if (m >= p.M) continue;
+          const float rsm = (p.rs && first) ? p.rs[m] : 0.f;
+          float v[8];
+          const float4 x0 = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + col);
+          const float4 x1 = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + col + 4);
+          v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) if (n + j < p.N) atomicAdd(cp + j, v[j]);
-        } else if (p.c_is_bf16) {
-          __nv_bfloat16* cp = (__nv_bfloat16*)p.C + (long)m * p.ldc + n;
-          if (full && ((p.ldc & 7) == 0)) {
-            if (p.accumulate) {
-              float old[8];
-              Act<__nv_bfloat16>::load8(cp, old);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += old[j];
-            }
-            Act<__nv_bfloat16>::store8(cp, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (n + j < p.N) cp[j] = __float2bfloat16_rn(p.accumulate ? v[j] + __bfloat162float(cp[j]) : v[j]);
+          for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(rsm, rcv[j], v[j] + bv[j]);
+            if (p.relu) v[j] = fmaxf(v[j], 0.f);
           }
-        } else {
-          float* cp = (float*)p.C + (long)m * p.ldc + n;
-          if (full && ((p.ldc & 3) == 0)) {
-            if (p.accumulate) {
-              float old[8];
-              Act<float>::load8(cp, old);
+          if (p.c_is_bf16) {
+            __nv_bfloat16* cp = (__nv_bfloat16*)p.C + (long)m * p.ldc + n;
+            if (full && ((p.ldc & 7) == 0)) {
+              if (p.accumulate) {
+                float old[8];
+                Act<__nv_bfloat16>::load8(cp, old);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += old[j];
+                for (int j = 0; j < 8; ++j) v[j] += old[j];
+              }
+              Act<__nv_bfloat16>::store8(cp, v);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) cp[j] = __float2bfloat16_rn(p.accumulate ? v[j] + __bfloat162float(cp[j]) : v[j]);
             }
-            Act<float>::store8(cp, v);
           } else {
+            float* cp = (float*)p.C + (long)m * p.ldc + n;
+            if (full && ((p.ldc & 3) == 0)) {
+              if (p.accumulate) {
+                float old[8];
+                Act<float>::load8(cp, old);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (n + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+                for (int j = 0; j < 8; ++j) v[j] += old[j];
+              }
+              Act<float>::store8(cp, v);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (n + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+            }
           }
         }
       }
+      __syncwarp();                                 // staging block free for the next column pass
     }
   }
   tc_fence_before();
@@ -322,15 +326,18 @@ int make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, i
 
 template <int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+  // two CTAs per SM: 2 stages x 48 KB for the 128x256 tile, 3 stages for the narrower ones (K = 256 is only
+  // four k-blocks, so depth matters less than letting one CTA's epilogue overlap the other's main loop)
+  constexpr int STAGES = BN == 256 ? 2 : 3;
   const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
     attr = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
   return FIRA_OK;
 }
 
