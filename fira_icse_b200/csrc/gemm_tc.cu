@@ -324,11 +324,8 @@ int make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, i
   return FIRA_OK;
 }
 
-template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
-  // two CTAs per SM: 2 stages x 48 KB for the 128x256 tile, 3 stages for the narrower ones (K = 256 is only
-  // four k-blocks, so depth matters less than letting one CTA's epilogue overlap the other's main loop)
-  constexpr int STAGES = BN == 256 ? 2 : 3;
+template <int BN, int STAGES>
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -339,6 +336,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cuda
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
   gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
   return FIRA_OK;
+}
+
+// Two launch shapes per tile width (measured, profiles/ + DESIGN.md):
+//   more CTAs than SMs -> shallow ring (2 x 48 KB for the 128x256 tile), TWO CTAs per SM: one CTA's epilogue
+//                         overlaps the other's TMA/MMA phase (GCN 325-CTA GEMM 30 -> 24 us, KV 145 -> 98 us);
+//   at most one wave   -> 4-stage ring, one CTA per SM: all four k-blocks of a K = 256 product are in flight at
+//                         once, which is what the latency-bound 15-105 CTA launches of the decoder need.
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+  const long ctas = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
+  if (ctas > 148) return launch_cfg<BN, (BN == 256 ? 2 : 3)>(ta, tb, p, st);
+  return launch_cfg<BN, 4>(ta, tb, p, st);
 }
 
 }  // namespace
