@@ -90,11 +90,15 @@ class TransModel(nn.Module):
         sou, tar, mark, ast_change, tar_label, sub_token = (
             t.to(dev, non_blocking=True) for t in (sou, tar, mark, ast_change, tar_label, sub_token))
         mem_mask = torch.cat((sou != 0, sub_token != 0), dim=1)
+        bf16 = self.precision == "bf16"
+        self.decoder.prefetch_weights()          # decoder / head weight preparation overlaps with the encoder
+        pf_head = ops.prefetch_head(bf16, self.out_fc.weight, self.copy_net.LinearSource.weight,
+                                    self.copy_net.LinearTarget.weight) if sou.is_cuda else None
         memory = self.encoder.encode_memory(sou, mark, ast_change, edge, sub_token)
         dec = self.decoder(tar, memory, mem_mask, tar != 0)
         label = self.shifted_label(tar_label)
         want_ids = stage != "train"
-        loss_sum, _, ids = ops.HeadFn.apply(want_ids, self.precision == "bf16", memory, dec, _u8(mem_mask),
+        loss_sum, _, ids = ops.HeadFn.apply(want_ids, bf16, pf_head, memory, dec, _u8(mem_mask),
                                             _i32(label).view(-1),
                                             self.out_fc.weight, self.out_fc.bias, *self.copy_net.flat_params())
         if stage == "train":

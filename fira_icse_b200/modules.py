@@ -205,14 +205,26 @@ class Decoder(nn.Module):
             [Attention(dmodel=args.embedding_dim, num_head=args.num_head) for _ in range(6)])
         self.feed_forward_list = nn.ModuleList([FeedForward(args.embedding_dim) for _ in range(6)])
 
+    def _flat(self):
+        lp = []
+        for a, c, f in zip(self.attention_list, self.cross_attention_list, self.feed_forward_list):
+            lp += a.flat_params() + c.flat_params() + f.flat_params()
+        return lp
+
+    def prefetch_weights(self):
+        """Start this decoder's weight preparation on the side stream (TransModel.forward calls it before
+        the encoder so that it overlaps with the encoder); the next forward() consumes it."""
+        dev = self.embedding.weight.device
+        if dev.type == "cuda":
+            self._prefetched = ops.prefetch_decoder(bool(getattr(self, "bf16", False)), self._flat(), dev)
+
     def forward(self, output_token, input_em, sou_mask, tar_mask_pad):
         dev = self.embedding.weight.device
         if self.pos_encode.device != dev:
             self.pos_encode = self.pos_encode.to(dev)
         cfg = _run_cfg(self)
-        cfg.update(p_dec=self.attention_list[0].dropout.p)
-        lp = []
-        for a, c, f in zip(self.attention_list, self.cross_attention_list, self.feed_forward_list):
-            lp += a.flat_params() + c.flat_params() + f.flat_params()
+        cfg.update(p_dec=self.attention_list[0].dropout.p, prefetch=getattr(self, "_prefetched", None))
+        self._prefetched = None
+        lp = self._flat()
         return ops.DecoderFn.apply(cfg, _i32(output_token), input_em, _u8(sou_mask), _u8(tar_mask_pad),
                                    self.pos_encode, self.embedding.weight, *lp)

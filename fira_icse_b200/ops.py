@@ -232,6 +232,70 @@ class Fork:
         self.keep.clear()
 
 
+class Prefetch:
+    """Weight-side preparation (concatenations, W2 @ W1 merges, the 4-row value table, bf16 operand copies)
+    issued on the side stream so it runs while the main stream computes; `event` marks completion."""
+
+    def __init__(self):
+        self.wcache = {}
+        self.items = None
+        self.event = None
+
+
+def _prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2):
+    f32 = dict(dtype=torch.float32, device=Wq.device)
+    Wqk = torch.cat((Wq, Wk), 0)
+    bqk = torch.cat((bq, bk), 0)
+    Vtab = linear(mark_emb, Wv, bv)                                # fp32 [4, 256]: value has 4 distinct rows
+    Wc = torch.empty((D, D), **f32)                                # W2 @ W1
+    gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=1)
+    c1 = torch.empty((D,), **f32)                                  # W2 @ b1
+    gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
+    for w in (Wqk, Wo, Wc):
+        pr.w(w)                                                    # bf16 operand copies (no-op in fp32 mode)
+    return Wqk, bqk, Vtab, Wc, c1
+
+
+def prefetch_decoder(bf16, lp, device):
+    """Called by TransModel.forward BEFORE the encoder runs: the decoder's weight preparation (12-way K/V
+    concatenation, per-layer QKV concatenations, ~40 bf16 casts) overlaps with the encoder."""
+    pf = Prefetch()
+    pr = Prec(bf16, pf.wcache)
+    L = len(lp) // DEC_LAYER_PARAMS
+    fork = Fork(device)
+    with fork(*lp):
+        Wkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])], 0)     # [L*512, 256]
+        bkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])], 0)
+        pr.w(Wkv)
+        layers = []
+        for i in range(L):
+            q = lp[i * 26:(i + 1) * 26]
+            Wqkv = torch.cat((q[0], q[2], q[4]), 0)
+            bqkv = torch.cat((q[1], q[3], q[5]), 0)
+            for w in (Wqkv, q[6], q[10], q[16], q[20], q[22]):     # Wqkv, self Wo, cross Wq, cross Wo, W1, W2
+                pr.w(w)
+            layers.append((Wqkv, bqkv))
+        pf.items = (Wkv, bkv, layers)
+        pf.event = torch.cuda.Event()
+        pf.event.record()
+    pf.fork = fork                                                 # keeps the inputs alive; joined by the consumer
+    return pf
+
+
+def prefetch_head(bf16, Wout, Ws, Wt):
+    pf = Prefetch()
+    if bf16:
+        pr = Prec(True, pf.wcache)
+        fork = Fork(Wout.device)
+        with fork(Wout, Ws, Wt):
+            for w in (Wout, Ws, Wt):
+                pr.w(w)
+            pf.event = torch.cuda.Event()
+            pf.event.record()
+        pf.fork = fork
+    return pf
+
+
 def make_seed():
     """64-bit dropout seed drawn from torch's CPU generator (so torch.manual_seed controls it)."""
     return int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -274,14 +338,24 @@ class EncoderFn(torch.autograd.Function):
              _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
         rs = edges.rowsum(n_code, n_sub, n_ast)
         saved = []
+        # weight-only work of ALL layers goes to the side stream, layer 0 first; the main stream waits for
+        # layer i's event right before it needs it, so only the first layer's ~8 tiny launches are exposed
+        fork = Fork(dev)
+        preps, events = [], []
+        with fork(mark_emb, *lp):
+            for i in range(L):
+                Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
+                preps.append(_prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2))
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
         for i in range(L):
             Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
             sid = cfg["stream_base"] + i * 8
+            torch.cuda.current_stream().wait_event(events[i])
+            Wqk, bqk, Vtab, Wc, c1 = preps[i]
             # ---- Combination (gnn_transformer.py:192-205, combination_layer.py:7-17)
-            Wqk = torch.cat((Wq, Wk), 0)
-            bqk = torch.cat((bq, bk), 0)
             QK = pr.linear(Xc, Wqk, bqk)                               # [Mc, 512] = [q | k]
-            Vtab = linear(mark_emb, Wv, bv)                            # fp32 [4, 256]: value has 4 distinct rows
             Cd = pr.empty((Mc, D), dev)
             call("fira_comb_gate_fwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(Cd), Mc, D, D // heads,
                  float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
@@ -291,10 +365,6 @@ class EncoderFn(torch.autograd.Function):
             G = pr.empty((R, D), dev)
             call("fira_gcn_aggregate", _ptr(edges.rowptr), _ptr(edges.col), _ptr(edges.val), _ptr(Gin), None,
                  _ptr(G), B, n_code, n_sub, n_ast, D, pr.code, st)
-            Wc = torch.empty((D, D), **f32)                            # W2 @ W1
-            gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=1)
-            c1 = torch.empty((D,), **f32)                              # W2 @ b1
-            gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
             Z = pr.linear(G, Wc, b2, rs=rs, rc=c1)
             Xc_n = pr.empty((Mc, D), dev)
             Gin_n = pr.empty((R, D), dev)
@@ -303,6 +373,7 @@ class EncoderFn(torch.autograd.Function):
             Xc, Gin = Xc_n, Gin_n
         memory = pr.empty((B, n_code + n_sub, D), dev)
         call("fira_pack_memory", _ptr(Xc), _ptr(Gin), _ptr(memory), B, n_code, n_sub, D, pr.code, st)
+        fork.join()
 
         ctx.saved = saved
         ctx.wcache = pr.wcache
@@ -410,8 +481,13 @@ class DecoderFn(torch.autograd.Function):
 
         X = pr.empty((Mt, D), dev)
         call("fira_embed_rows_fwd", _ptr(tar), _ptr(dec_emb), _ptr(pos_table), _ptr(X), Mt, T, D, pr.code, st)
-        Wkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])], 0)     # [L*512, 256]
-        bkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])], 0)
+        pf = cfg.get("prefetch")
+        if pf is None:
+            pf = prefetch_decoder(pr.bf16, lp, dev)
+        torch.cuda.current_stream().wait_event(pf.event)
+        pf.fork.join()
+        pr.wcache.update(pf.wcache)
+        Wkv, bkv, qkv_layers = pf.items
         ldkv = L * 2 * D
         KV = pr.linear(memory.view(Ms, D), Wkv, bkv)                                              # [Ms, L*512]
         saved = []
@@ -421,8 +497,7 @@ class DecoderFn(torch.autograd.Function):
              fW1, fb1, fW2, fb2, flw, flb) = lp[i * 26:(i + 1) * 26]
             sid = cfg["stream_base"] + 64 + i * 8
             # ---- masked self-attention (gnn_transformer.py:117-119)
-            Wqkv = torch.cat((sWq, sWk, sWv), 0)
-            bqkv = torch.cat((sbq, sbk, sbv), 0)
+            Wqkv, bqkv = qkv_layers[i]
             QKV = pr.linear(X, Wqkv, bqkv)                               # [Mt, 768]
             ctx1 = pr.empty((Mt, D), dev)
             st1 = torch.empty((B, H, T, 2), **f32)
@@ -557,13 +632,17 @@ class HeadFn(torch.autograd.Function):
     is never built."""
 
     @staticmethod
-    def forward(ctx, want_argmax, bf16, memory, dec, mem_mask, label, Wout, bout, Ws, Wt, Wres, bres, Wp, bp):
+    def forward(ctx, want_argmax, bf16, pf, memory, dec, mem_mask, label, Wout, bout, Ws, Wt, Wres, bres, Wp, bp):
         _require_cuda(memory, dec, Wout)
         B, S, _ = memory.shape
         T = dec.shape[1]
         V = Wout.shape[0]
         Mt, Ms = B * T, B * S
         pr = Prec(bf16)
+        if pf is not None and pf.event is not None:
+            torch.cuda.current_stream().wait_event(pf.event)
+            pf.fork.join()
+            pr.wcache.update(pf.wcache)
         dev = dec.device
         f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
@@ -635,7 +714,7 @@ class HeadFn(torch.autograd.Function):
         linear_dx(dgl, 2, Wp, Mt, out=d_dec, accumulate=True)
         linear_dx(d_tgt, D, Wt, Mt, out=d_dec, accumulate=True)
         fork.join()
-        return (None, None, d_mem.view(B, S, D).to(mem_dt), d_dec.view(B, T, D).to(dec_dt), None, None, d_Wout, d_bout,
+        return (None, None, None, d_mem.view(B, S, D).to(mem_dt), d_dec.view(B, T, D).to(dec_dt), None, None, d_Wout, d_bout,
                 d_Ws, d_Wt, d_wres, d_bres, d_Wp, d_bp)
 
 

@@ -62,7 +62,7 @@ def test_intermediates_match_reference(model, gold):
         dec = model.decoder(tar, memory, mem_mask, tar != 0)
         logits = model.out_fc(dec)
         scores, gate = model.copy_net(memory, dec)
-        _, nll, _ = ops.HeadFn.apply(False, False, memory, dec, mem_mask.to(torch.uint8),
+        _, nll, _ = ops.HeadFn.apply(False, False, None, memory, dec, mem_mask.to(torch.uint8),
                                      model.shifted_label(tar_label).to(torch.int32).view(-1),
                                      model.out_fc.weight, model.out_fc.bias, *model.copy_net.flat_params())
     real = mem_mask[:4].unsqueeze(-1).cpu().numpy()
