@@ -255,6 +255,50 @@ def spmm_roofline(dev, hb, B):
             "l2": f"cold: {n_pairs} rotating buffer pairs ({n_pairs * 2 * R * 1024 / 1e6:.0f} MB > 126 MB L2)"}
 
 
+# ------------------------------------------------------------------------------------------------ GEMM roofline
+def gemm_roofline(dev, B):
+    """The kernel with the largest share of the bf16 step is the tcgen05 GEMM; time its most frequent large
+    shape live (the GCN layer product: [B*650, 256] x [256, 256]^T, bf16 in/out) with CUDA events on rotating
+    buffers (> L2) and report it against BOTH measured peaks (it is HBM-bound by arithmetic intensity)."""
+    import torch
+    from fira_icse_b200 import ops
+    M, N, K = B * 650, 256, 256
+    n_buf = max(3, int(400e6 // (2 * M * 256 * 2)) + 1)
+    xs = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(n_buf)]
+    ys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(n_buf)]
+    W = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    st = torch.cuda.current_stream()
+    for i in range(6):
+        ops.gemm_tc(xs[i % n_buf], K, 1, W, K, 1, ys[i % n_buf], N, M, N, K, bias=bias)
+    iters = 40
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for i in range(iters):
+        ev[i][0].record(st)
+        ops.gemm_tc(xs[i % n_buf], K, 1, W, K, 1, ys[i % n_buf], N, M, N, K, bias=bias)
+        ev[i][1].record(st)
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    avg = sum(ms) / len(ms)
+    alg_bytes = (M * K + N * K + M * N) * 2 + N * 4
+    flops = 2.0 * M * N * K
+    hbm, how = measured_peaks()
+    tf_peak = 1645.8
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        tf_peak = float(json.load(open(path)).get("bf16_tflops", tf_peak))
+    gbs = alg_bytes / (avg * 1e-3) / 1e9
+    tfs = flops / (avg * 1e-3) / 1e12
+    return {"kernel": "gemm_tc_kernel<256> (fira_gemm_bf16_tc), GCN layer product", "shape": [M, N, K],
+            "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+            "achieved_tflops": tfs, "peak_tflops": tf_peak, "frac_tensor": tfs / tf_peak,
+            "algorithmic_bytes_per_launch": alg_bytes, "flops_per_launch": flops, "avg_launch_ms": avg,
+            "launches_timed": iters, "peak_source": how,
+            "note": "arithmetic intensity 2*256/(2+2+~0) ~ 128 FLOP/B < ridge ~250: HBM roofline applies; the launch is "
+                    "latency-bound (K = 256 = four k-blocks per tile), see profiles/gemm_tc_r1_ncu_details.txt"}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args):
     import torch
@@ -389,6 +433,7 @@ def run_gpu_arm(args):
         return
 
     roof = spmm_roofline(dev, pool_host[0], B)
+    roof_gemm = gemm_roofline(dev, B) if args.precision == "bf16" else None
 
     # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of 16 commits)
     cpu_info = None
@@ -425,7 +470,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "api": "TransModel.forward(sou,tar,attr,mark,ast_change,PackedEdges,tar_label,sub_token,'train')"},
             "e2e_dense_edge": dense_info,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm,
             "cpu_baseline": cpu_info, "last_loss": last_loss[0]}
     print(json.dumps(line), flush=True)
     if world > 1:

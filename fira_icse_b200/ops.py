@@ -22,6 +22,11 @@ from ._lib import FIRA_BF16, FIRA_F32, call
 
 D = 256
 
+# gradients produced on the side stream are consumed by AccumulateGrad on the main stream after Fork.join():
+# the stream mismatch autograd warns about is intentional
+if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
