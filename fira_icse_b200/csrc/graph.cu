@@ -260,58 +260,49 @@ __global__ void __launch_bounds__(256) csr_spmm_rows_kernel(const int* __restric
 // fp32).  A warp then carries two independent rows, i.e. twice the rows -- and twice the dependent
 // rowptr -> (col,val) -> feature-row chains -- in flight for the same number of resident warps; the bf16
 // rows (512 B) are too short for a full warp to keep enough bytes in flight (v1: 0.29 of peak in bf16).
-template <typename T>
-__global__ void __launch_bounds__(256) csr_spmm_half_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+template <typename T, int LPR>     // LPR lanes per destination row (16 or 8): 32/LPR rows in flight per warp
+__global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                             const float* __restrict__ val, const T* __restrict__ x,
                                                             const T* __restrict__ addend, T* __restrict__ y, Segs s,
                                                             int N) {
+  constexpr int F = D / LPR;                      // features per lane (16 or 32)
+  constexpr int RPW = 32 / LPR;                   // rows per warp
   const long R = (long)s.B * N;
   const int lane = threadIdx.x & 31;
-  const int hl = lane & 15;                       // lane within the half warp
-  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
-  const int hbase = lane & 16;                    // shuffle source offset of this half
-  const long half0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
-  const long nhalves = (long)gridDim.x * (blockDim.x >> 5) * 2;
-  for (long r = half0; r < R; r += nhalves) {
+  const int hl = lane % LPR;                      // lane within its row group
+  const int hbase = lane - hl;                    // shuffle source offset of this group
+  const unsigned hmask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << hbase;
+  const long part0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const long nparts = (long)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (long r = part0; r < R; r += nparts) {
     int b, i; seg_unrow(s, r, b, i);
     const long g = (long)b * N + i;
     const int e0 = rowptr[g], e1 = rowptr[g + 1];
-    float acc[16];
-    if (addend) { Act<T>::load8(addend + r * D + hl * 16, acc); Act<T>::load8(addend + r * D + hl * 16 + 8, acc + 8); }
-    else {
+    float acc[F];
+    if (addend) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      for (int q = 0; q < F; q += 8) Act<T>::load8(addend + r * D + hl * F + q, acc + q);
+    } else {
+#pragma unroll
+      for (int k = 0; k < F; ++k) acc[k] = 0.f;
     }
-    for (int eb = e0; eb < e1; eb += 16) {
-      const int n = min(16, e1 - eb);
+    for (int eb = e0; eb < e1; eb += LPR) {
+      const int n = min(LPR, e1 - eb);
       int c = 0; float w = 0.f;
       if (hl < n) { c = col[eb + hl]; w = val[eb + hl]; }
-      int t = 0;
-      for (; t + 1 < n; t += 2) {
-        const int c0 = __shfl_sync(hmask, c, hbase + t), c1 = __shfl_sync(hmask, c, hbase + t + 1);
-        const float w0 = __shfl_sync(hmask, w, hbase + t), w1 = __shfl_sync(hmask, w, hbase + t + 1);
-        float v0[16], v1[16];
-        const T* p0 = x + seg_row(s, b, c0) * D + hl * 16;
-        const T* p1 = x + seg_row(s, b, c1) * D + hl * 16;
-        Act<T>::load8(p0, v0); Act<T>::load8(p0 + 8, v0 + 8);
-        Act<T>::load8(p1, v1); Act<T>::load8(p1 + 8, v1 + 8);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = fmaf(w1, v1[k], acc[k]);
-      }
-      if (t < n) {
+      for (int t = 0; t < n; ++t) {
         const int c0 = __shfl_sync(hmask, c, hbase + t);
         const float w0 = __shfl_sync(hmask, w, hbase + t);
-        float v0[16];
-        const T* p0 = x + seg_row(s, b, c0) * D + hl * 16;
-        Act<T>::load8(p0, v0); Act<T>::load8(p0 + 8, v0 + 8);
+        float v0[F];
+        const T* p0 = x + seg_row(s, b, c0) * D + hl * F;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
+        for (int q = 0; q < F; q += 8) Act<T>::load8(p0 + q, v0 + q);
+#pragma unroll
+        for (int k = 0; k < F; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
       }
     }
-    Act<T>::store8(y + r * D + hl * 16, acc);
-    Act<T>::store8(y + r * D + hl * 16 + 8, acc + 8);
+#pragma unroll
+    for (int q = 0; q < F; q += 8) Act<T>::store8(y + r * D + hl * F + q, acc + q);
   }
 }
 
@@ -501,12 +492,18 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     int grid = (int)(ctas < cap ? ctas : cap);
     DISPATCH_T(dtype, csr_spmm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, (const T*)x,
                                                                                    (const T*)addend, (T*)y, s, N);)
-  } else if (variant == 4) {
-    long ctas = (R + 15) / 16;               // 8 warps x 2 rows
+  } else if (variant == 4 || variant == 5) {
+    const int rpw = variant == 4 ? 2 : 4;
+    long ctas = (R + 8 * rpw - 1) / (8 * rpw);
     const long cap = 148L * 8 * 4;
     int grid = (int)(ctas < cap ? ctas : cap);
-    DISPATCH_T(dtype, csr_spmm_half_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    if (variant == 4) {
+      DISPATCH_T(dtype, csr_spmm_part_kernel<T, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    } else {
+      DISPATCH_T(dtype, csr_spmm_part_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    }
   } else if (variant == 3) {
     constexpr int WARPS = 6;
     const size_t smem = (size_t)WARPS * EB * D * (dtype == FIRA_F32 ? 4 : 2);
