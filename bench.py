@@ -210,7 +210,7 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-def spmm_roofline(dev, hb, B):
+def spmm_roofline(dev, hb, B, bf16=False):
     """Time fira_gcn_aggregate alone (CUDA events on the launching stream), cold L2: the launches rotate
     through buffer pairs whose total size exceeds the 126 MB L2."""
     import torch
@@ -221,13 +221,15 @@ def spmm_roofline(dev, hb, B):
     pe = PackedEdges.from_host(rowptr, col, val, B, N_NODES, dev)
     R = B * N_NODES
     n_pairs = max(3, int(400e6 // (2 * R * 256 * 4)) + 1)
-    xs = [torch.randn(R, 256, device=dev) for _ in range(n_pairs)]
-    ys = [torch.empty(R, 256, device=dev) for _ in range(n_pairs)]
+    tdt, esz, code = (torch.bfloat16, 2, 1) if bf16 else (torch.float32, 4, 0)
+    n_pairs = max(3, int(400e6 // (2 * R * 256 * esz)) + 1)
+    xs = [torch.randn(R, 256, device=dev).to(tdt) for _ in range(n_pairs)]
+    ys = [torch.empty(R, 256, device=dev, dtype=tdt) for _ in range(n_pairs)]
     st = torch.cuda.current_stream()
 
     def launch(i):
         _lib.call("fira_gcn_aggregate", pe.rowptr.data_ptr(), pe.col.data_ptr(), pe.val.data_ptr(),
-                  xs[i % n_pairs].data_ptr(), None, ys[i % n_pairs].data_ptr(), B, N_CODE, N_SUB, N_AST, 256, 0,
+                  xs[i % n_pairs].data_ptr(), None, ys[i % n_pairs].data_ptr(), B, N_CODE, N_SUB, N_AST, 256, code,
                   st.cuda_stream)
     for i in range(6):
         launch(i)
@@ -241,18 +243,20 @@ def spmm_roofline(dev, hb, B):
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     avg_ms = sum(ms) / len(ms)
-    alg_bytes = 2 * R * 256 * 4 + (R + 1) * 4 + pe.nnz * 8          # SURVEY.md section 8d formula, fp32
+    alg_bytes = 2 * R * 256 * esz + (R + 1) * 4 + pe.nnz * 8        # SURVEY.md section 8d formula
     peak, how = measured_peaks()
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not bf16:
         traffic = json.load(open(tpath)).get("fira_gcn_aggregate_dram_bytes_per_launch")
-    return {"bound": "hbm", "kernel": "csr_spmm_kernel<float> (fira_gcn_aggregate)", "achieved": achieved,
+    kname = "csr_spmm_part_kernel<bf16,16>" if bf16 else "csr_spmm_kernel<float>"
+    return {"bound": "hbm", "kernel": kname + " (fira_gcn_aggregate, the GNN scatter)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "median_launch_ms": ms[len(ms) // 2],
             "launches_timed": iters, "rows": R, "nnz": pe.nnz, "peak_source": how,
-            "l2": f"cold: {n_pairs} rotating buffer pairs ({n_pairs * 2 * R * 1024 / 1e6:.0f} MB > 126 MB L2)"}
+            "dtype": "bf16" if bf16 else "f32",
+            "l2": f"cold: {n_pairs} rotating buffer pairs ({n_pairs * 2 * R * 256 * esz / 1e6:.0f} MB > 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------------------ GEMM roofline
@@ -432,7 +436,8 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    roof = spmm_roofline(dev, pool_host[0], B)
+    roof = spmm_roofline(dev, pool_host[0], B, bf16=args.precision == "bf16")
+    roof_f32 = spmm_roofline(dev, pool_host[0], B, bf16=False) if args.precision == "bf16" else None
     roof_gemm = gemm_roofline(dev, B) if args.precision == "bf16" else None
 
     # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of 16 commits)
@@ -470,7 +475,8 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "api": "TransModel.forward(sou,tar,attr,mark,ast_change,PackedEdges,tar_label,sub_token,'train')"},
             "e2e_dense_edge": dense_info,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_scatter_fp32": roof_f32,
+            "roofline_gemm": roof_gemm,
             "cpu_baseline": cpu_info, "last_loss": last_loss[0]}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -175,87 +175,6 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(const int* __restrict__ r
   }
 }
 
-// Version 2 (what fira_gcn_aggregate launches): the row-at-a-time kernel above is latency-bound
-// (rowptr -> col/val -> feature row are three dependent DRAM round trips per row and FIRA rows have
-// ~1.6 neighbours, ncu round 1: 50 % warps active, 25 % DRAM).  Here a warp owns RPW consecutive
-// destination rows and runs each phase for all of them before the next one, so RPW independent
-// 1 KB row reads are in flight per warp:
-//   phase 1  lanes 0..RPW-1 fetch (rowptr[g], rowptr[g+1]) of their row
-//   phase 2  per row, lanes fetch its (col, val) chunk (<= 32 edges) -- RPW coalesced loads back to back
-//   phase 3  edge t of every row: RPW predicated feature-row loads issued together, then the FMAs
-// Rows longer than 32 edges loop over chunks.  Same source-order fp32 accumulation as v1.
-constexpr int RPW = 4;
-
-template <typename T>
-__global__ void __launch_bounds__(256) csr_spmm_rows_kernel(const int* __restrict__ rowptr,
-                                                            const int* __restrict__ col,
-                                                            const float* __restrict__ val, const T* __restrict__ x,
-                                                            const T* __restrict__ addend, T* __restrict__ y, Segs s,
-                                                            int N) {
-  const long R = (long)s.B * N;
-  const int lane = threadIdx.x & 31;
-  const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
-  for (long r0 = warp0 * RPW; r0 < R; r0 += nwarps * RPW) {
-    // phase 1
-    int my_e0 = 0, my_e1 = 0, my_b = 0;
-    if (lane < RPW && r0 + lane < R) {
-      int b, i; seg_unrow(s, r0 + lane, b, i);
-      const long g = (long)b * N + i;
-      my_e0 = rowptr[g]; my_e1 = rowptr[g + 1]; my_b = b;
-    }
-    int e0[RPW], e1[RPW], bb[RPW];
-    float acc[RPW][8];
-#pragma unroll
-    for (int j = 0; j < RPW; ++j) {
-      e0[j] = __shfl_sync(0xffffffffu, my_e0, j);
-      e1[j] = __shfl_sync(0xffffffffu, my_e1, j);
-      bb[j] = __shfl_sync(0xffffffffu, my_b, j);
-      if (addend && r0 + j < R) Act<T>::load8(addend + (r0 + j) * D + lane * 8, acc[j]);
-      else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
-      }
-    }
-    bool more = true;
-    while (more) {
-      // phase 2: one chunk of <= 32 edges per row
-      int c[RPW], n[RPW]; float w[RPW];
-      int nmax = 0;
-#pragma unroll
-      for (int j = 0; j < RPW; ++j) {
-        n[j] = min(32, e1[j] - e0[j]);
-        c[j] = 0; w[j] = 0.f;
-        if (lane < n[j]) { c[j] = col[e0[j] + lane]; w[j] = val[e0[j] + lane]; }
-        nmax = max(nmax, n[j]);
-      }
-      // phase 3
-      for (int t = 0; t < nmax; ++t) {
-        float v[RPW][8];
-        float wt[RPW];
-#pragma unroll
-        for (int j = 0; j < RPW; ++j) {
-          const int cj = __shfl_sync(0xffffffffu, c[j], t);
-          wt[j] = __shfl_sync(0xffffffffu, w[j], t);
-          if (t < n[j]) Act<T>::load8(x + seg_row(s, bb[j], cj) * D + lane * 8, v[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < RPW; ++j)
-          if (t < n[j]) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(wt[j], v[j][k], acc[j][k]);
-          }
-      }
-      more = false;
-#pragma unroll
-      for (int j = 0; j < RPW; ++j) { e0[j] += n[j]; more |= (e0[j] < e1[j]); }
-    }
-#pragma unroll
-    for (int j = 0; j < RPW; ++j)
-      if (r0 + j < R) Act<T>::store8(y + (r0 + j) * D + lane * 8, acc[j]);
-  }
-}
-
 // Version 4: HALF a warp per destination row, 16 features per lane (two 16-byte loads for bf16, four for
 // fp32).  A warp then carries two independent rows, i.e. twice the rows -- and twice the dependent
 // rowptr -> (col,val) -> feature-row chains -- in flight for the same number of resident warps; the bf16
@@ -485,25 +404,22 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
   Segs s{B, n_code, n_sub, n_ast};
   const int N = n_code + n_sub + n_ast;
   const long R = (long)B * N;
-  static const int variant = [] { const char* e = getenv("FIRA_SPMM_VARIANT"); return e ? atoi(e) : 1; }();
+  // measured defaults (profiles/spmm_variants_r1.md): fp32 rows (1 KB) -> one warp per row; bf16 rows (512 B) ->
+  // half a warp per row (two rows in flight per warp: 23 -> 19 us at B = 64).  FIRA_SPMM_VARIANT overrides (A/B runs).
+  static const int forced = [] { const char* e = getenv("FIRA_SPMM_VARIANT"); return e ? atoi(e) : 0; }();
+  const int variant = forced ? forced : (dtype == FIRA_BF16 ? 4 : 1);
   if (variant == 1) {                      // round-1 baseline kernel, kept for A/B profiling
     long ctas = (R + 7) / 8;
     const long cap = 148L * 8 * 4;
     int grid = (int)(ctas < cap ? ctas : cap);
     DISPATCH_T(dtype, csr_spmm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, (const T*)x,
                                                                                    (const T*)addend, (T*)y, s, N);)
-  } else if (variant == 4 || variant == 5) {
-    const int rpw = variant == 4 ? 2 : 4;
-    long ctas = (R + 8 * rpw - 1) / (8 * rpw);
+  } else if (variant == 4) {
+    long ctas = (R + 15) / 16;               // 8 warps x 2 rows
     const long cap = 148L * 8 * 4;
     int grid = (int)(ctas < cap ? ctas : cap);
-    if (variant == 4) {
-      DISPATCH_T(dtype, csr_spmm_part_kernel<T, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
-    } else {
-      DISPATCH_T(dtype, csr_spmm_part_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
-    }
+    DISPATCH_T(dtype, csr_spmm_part_kernel<T, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else if (variant == 3) {
     constexpr int WARPS = 6;
     const size_t smem = (size_t)WARPS * EB * D * (dtype == FIRA_F32 ? 4 : 2);
@@ -521,11 +437,8 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     DISPATCH_T(dtype, csr_spmm_bulk_kernel<T, WARPS><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else {
-    long ctas = (R + 8 * RPW - 1) / (8 * RPW);
-    const long cap = 148L * 16;            // multiple of the SM count; grid-stride beyond
-    int grid = (int)(ctas < cap ? ctas : cap);
-    DISPATCH_T(dtype, csr_spmm_rows_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    fira_set_error(FIRA_ERR_ARG, "gcn_aggregate: unknown FIRA_SPMM_VARIANT %d (1, 3, 4)", variant);
+    return FIRA_ERR_ARG;
   }
   FIRA_CHECK_LAUNCH("fira_gcn_aggregate");
   return FIRA_OK;
