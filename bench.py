@@ -85,15 +85,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ data
-def host_batch(first_index, batch_size, pin):
-    """One collated synthetic batch on the host: int64 id tensors + packed CSR (what a loader delivers)."""
+def host_batch(first_index, batch_size, pin, trim=False):
+    """One collated synthetic batch on the host: int64 id tensors + packed CSR (what a loader delivers).
+    trim=True: the loader also drops the padding the whole batch shares (data.trim_batch_host)."""
     import torch
+    from fira_icse_b200.data import trim_batch_host
     from fira_icse_b200.graph import PackedEdges
     from fira_icse_b200.synth import N_NODES, synth_batch
     ids, coo = synth_batch(first_index, batch_size, VOCAB, AST_VOCAB)
     t = {k: torch.from_numpy(v) for k, v in ids.items()}
     t["attr"] = torch.zeros(batch_size, 1, dtype=torch.int64)    # accepted and ignored by the model (Model.py:38)
     rowptr, col, val = PackedEdges.pack_host(coo, N_NODES, pin=False)
+    if trim:
+        lst = trim_batch_host([t["sou"], t["tar"], t["attr"], t["mark"], t["ast_change"], (rowptr, col, val),
+                               t["tar_label"], t["sub_token"]], VOCAB)
+        t = dict(zip(("sou", "tar", "attr", "mark", "ast_change", "_", "tar_label", "sub_token"), lst))
+        rowptr, col, val = t.pop("_")
     if pin:
         t = {k: v.pin_memory() for k, v in t.items()}
         rowptr, col, val = rowptr.pin_memory(), col.pin_memory(), val.pin_memory()
@@ -106,7 +113,8 @@ def device_batch(hb, dev, B):
     from fira_icse_b200.synth import N_NODES
     t, (rowptr, col, val), _ = hb
     d = {k: v.to(dev, non_blocking=True) for k, v in t.items()}
-    edges = PackedEdges.from_host(rowptr, col, val, B, N_NODES, dev)
+    n_nodes = t["sou"].shape[1] + t["sub_token"].shape[1] + t["ast_change"].shape[1]
+    edges = PackedEdges.from_host(rowptr, col, val, B, n_nodes, dev)
     return [d["sou"], d["tar"], d["attr"], d["mark"], d["ast_change"], edges, d["tar_label"], d["sub_token"]]
 
 
@@ -334,7 +342,8 @@ def run_gpu_arm(args):
     model.set_precision(args.precision)
 
     # every rank gets its own shard of the synthetic stream (graphs shard by commit, no data collective)
-    pool_host = [host_batch((rank * N_POOL + i) * B, B, pin=True) for i in range(N_POOL)]
+    pool_host = [host_batch((rank * N_POOL + i) * B, B, pin=True, trim=args.trim) for i in range(N_POOL)]
+    full_host = pool_host[0] if not args.trim else host_batch(rank * N_POOL * B, B, pin=True, trim=False)
     pool_dev = [device_batch(hb, dev, B) for hb in pool_host]
 
     def host_list(hb):
@@ -365,9 +374,10 @@ def run_gpu_arm(args):
         # whole step captured in a CUDA graph (fira_icse_b200/engine.py): one cudaGraphLaunch per step
         eng = GraphedTrainStep(model, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True))
         eng.load(pool_dev[0])
+        eng.capture()                                                # one eager step + capture of this shape
         c0 = _lib.LAUNCH_COUNT
-        eng.capture(warmup=3)
-        launches_per_step = (_lib.LAUNCH_COUNT - c0) // 4            # 3 warm-up iterations + the captured one
+        eng._forward_backward(eng.cur)                               # count the C-ABI calls of one step (eager)
+        launches_per_step = _lib.LAUNCH_COUNT - c0
         optimizer, bucket = eng.optimizer, eng.bucket
 
         def resident_step(i):
@@ -411,7 +421,7 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import fira_oracle as O
-        t, _, coo = pool_host[0]
+        t, _, coo = full_host
         dense = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo]).pin_memory()    # builds the INPUT only
 
         def dense_step(i):
@@ -436,8 +446,8 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    roof = spmm_roofline(dev, pool_host[0], B, bf16=args.precision == "bf16")
-    roof_f32 = spmm_roofline(dev, pool_host[0], B, bf16=False) if args.precision == "bf16" else None
+    roof = spmm_roofline(dev, full_host, B, bf16=args.precision == "bf16")
+    roof_f32 = spmm_roofline(dev, full_host, B, bf16=False) if args.precision == "bf16" else None
     roof_gemm = gemm_roofline(dev, B) if args.precision == "bf16" else None
 
     # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of 16 commits)
@@ -470,6 +480,11 @@ def run_gpu_arm(args):
                                           "fp32 parity (fp32 storage, fp32 FFMA accumulate)"),
                        "optimizer": "Adam lr 1e-4 (torch fused), dropout on (0.1 / GCN 0.2)",
                        "launch": "whole step replayed as one CUDA graph" if args.graph else "eager launches",
+                       "padding": ("loader trims the padding the batch shares (code/sub-token/AST segments cut to the "
+                                   "batch maximum, multiple of 8); real rows, loss and gradients unchanged"
+                                   if args.trim else "full 210/160/280 padding"),
+                       "batch_shapes": sorted({(hb[0]["sou"].shape[1], hb[0]["sub_token"].shape[1],
+                                                hb[0]["ast_change"].shape[1]) for hb in pool_host}),
                        "l2": f"{N_POOL} distinct batches rotated; one step touches >1 GB of activations (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "commits/s", "h2d_bytes_per_step": int(h2d_bytes(pool_host[0])),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
@@ -491,6 +506,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FIRA_PRECISION", "bf16"), choices=["bf16", "fp32"],
                     help="bf16 = BASELINE.json config (default); fp32 = parity mode")
+    ap.add_argument("--no-trim", dest="trim", action="store_false",
+                    help="feed fully padded 210/160/280 batches instead of loader-trimmed ones")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true",

@@ -21,8 +21,8 @@ def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, t
     dev = model.out_fc.weight.device
     sou, mark, ast_change, sub_token = (t.to(dev) for t in (sou, mark, ast_change, sub_token))
     B, K = sou.shape[0], beam_size
-    V, n_code = model.vocab_size, model.sou_len
-    C = V + n_code + model.sub_token_len
+    V, n_code = model.vocab_size, sou.shape[1]
+    C = V + n_code + sub_token.shape[1]
     memory = model.encoder.encode_memory(sou, mark, ast_change, edge, sub_token)        # once per batch
     mem_mask = torch.cat((sou != pad_id, sub_token != 0), dim=1)
     copy_src = torch.cat((sou, sub_token), dim=1)                                       # copy id -> vocabulary id

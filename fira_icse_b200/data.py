@@ -229,3 +229,41 @@ def batch_to_device(batch, device, n_nodes=650):
         else:
             out.append(o.to(device, non_blocking=True) if o is not None else None)
     return out
+
+
+def trim_batch_host(batch, vocab_size, multiple=8, full=(210, 160, 280)):
+    """Drop the padding the whole batch shares (var-len packing, SURVEY.md section 8f rank 4, loader side).
+
+    batch: collate_packed-style list [sou, tar, attr, mark, ast_change, (rowptr, col, val), tar_label, sub_token]
+    (host tensors, node lengths `full`).  Code / sub-token / AST+edit segments are cut to the longest
+    commit of the batch (rounded up to `multiple`); the adjacency rows of the removed nodes -- isolated
+    self-loop rows by construction (Dataset.py:271-275) -- are dropped, column ids and sub-token copy
+    labels are renumbered.  Real rows, loss and gradients are unchanged; the model takes the shorter
+    tensors as they are (all shapes are read from the inputs)."""
+    sou, tar, attr, mark, ast_change, (rowptr, col, val), tar_label, sub_token = batch
+    n0, n1, n2 = full
+    B = sou.shape[0]
+
+    def cap(t, n):
+        used = int((t != 0).sum(1).max()) if t.numel() else 0
+        return min(n, max(multiple, -(-used // multiple) * multiple))
+    c0, c1, c2 = cap(sou, n0), cap(sub_token, n1), cap(ast_change, n2)
+    N, Nt = n0 + n1 + n2, c0 + c1 + c2
+    keep = np.zeros(N, bool)
+    keep[:c0] = True; keep[n0:n0 + c1] = True; keep[n0 + n1:n0 + n1 + c2] = True
+    remap = np.full(N, -1, np.int64)
+    remap[keep] = np.arange(Nt)
+    rp = rowptr.numpy().astype(np.int64)
+    deg = np.diff(rp).reshape(B, N)
+    row_keep = np.broadcast_to(keep, (B, N)).reshape(-1)
+    entry_keep = np.repeat(row_keep, deg.reshape(-1))
+    new_col = remap[col.numpy()[entry_keep]]
+    assert (new_col >= 0).all(), "a kept node has a neighbour inside the trimmed padding: adjacency is not padding-isolated"
+    new_rowptr = np.concatenate((np.zeros(1, np.int64), np.cumsum(deg[:, keep].reshape(-1))))
+    label = tar_label.clone()
+    sub_copy = label >= vocab_size + n0
+    label[sub_copy] -= (n0 - c0)
+    out = [sou[:, :c0].contiguous(), tar, attr, mark[:, :c0].contiguous(), ast_change[:, :c2].contiguous(),
+           (torch.from_numpy(new_rowptr.astype(np.int32)), torch.from_numpy(new_col.astype(np.int32)),
+            torch.from_numpy(val.numpy()[entry_keep])), label, sub_token[:, :c1].contiguous()]
+    return out

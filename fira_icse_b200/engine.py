@@ -1,17 +1,21 @@
 """CUDA-graph training engine: the whole step (zero grads -> TransModel forward -> backward ->
-[all-reduce] -> Adam) is captured once and replayed, so the ~900 launches of a step cost one
-cudaGraphLaunch instead of ~900 Python/ctypes round trips (the bf16 step is launch-bound otherwise).
+[all-reduce] -> Adam) is captured once per input shape and replayed, so the ~700 launches of a step
+cost one cudaGraphLaunch instead of ~700 Python/ctypes round trips (the bf16 step is launch-bound
+otherwise).
 
 What makes the path capturable
   * every kernel is launched on the current stream through the C ABI, with caller-owned buffers
     (they come from the graph's private pool during capture) and no host synchronisation;
-  * inputs live in STATIC device buffers (ids, shifted labels, CSR arrays with a fixed edge capacity --
-    the kernels only walk rowptr ranges, so the tail of col/val is never read);
+  * inputs live in STATIC device buffers (ids, labels, CSR arrays with a fixed edge capacity -- the
+    kernels only walk rowptr ranges, so the tail of col/val is never read);
   * dropout masks are keyed by `seed + *seed_ctr`; the graph bumps the device counter on every replay,
     so replays draw fresh masks although the host-side seed is frozen into the graph;
-  * TMA tensor maps are kernel parameters, rebuilt at capture time for the pooled buffers.
-N > 1: the forward/backward graph, an eager NCCL all-reduce of the flat gradient bucket, then the
-optimizer graph (same numerics as parallel.DataParallelStep).
+  * TMA tensor maps are kernel parameters, rebuilt at capture time for the pooled buffers;
+  * weight-gradient work and weight preparation run on a forked stream = parallel graph branches.
+Batches whose padding was trimmed by the loader (data.trim_batch_host) come in a few distinct
+(n_code, n_sub, n_ast) shapes: one graph per shape, one shared optimizer.
+N > 1: forward/backward graph, eager NCCL all-reduce of ONE flat gradient buffer, optimizer graph
+(same numerics as parallel.DataParallelStep).
 """
 import torch
 import torch.distributed as dist
@@ -22,113 +26,152 @@ from .parallel import FlatGradBucket
 ID_KEYS = ("sou", "tar", "mark", "ast_change", "tar_label", "sub_token")
 
 
+class _Captured:
+    """Static buffers + graph of one input shape."""
+
+    def __init__(self, shapes, B, n_nodes, cap, dev):
+        self.ids = {k: torch.zeros((B, n), dtype=torch.int64, device=dev) for k, n in zip(ID_KEYS, shapes)}
+        self.rowptr = torch.zeros(B * n_nodes + 1, dtype=torch.int32, device=dev)
+        self.col = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.val = torch.zeros(cap, dtype=torch.float32, device=dev)
+        self.n_nodes, self.cap = n_nodes, cap
+        self.graph = None
+        self.grads = None
+
+
 class GraphedTrainStep:
-    def __init__(self, model, batch_size, optimizer_factory, edge_capacity=None, n_nodes=650, group=None,
-                 lens=(210, 30, 210, 280, 30, 160)):
-        self.model, self.B, self.N, self.group = model, batch_size, n_nodes, group
+    def __init__(self, model, batch_size, optimizer_factory, edge_capacity=None, group=None):
+        self.model, self.B, self.group = model, batch_size, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        dev = next(model.parameters()).device
-        self.dev = dev
+        self.dev = next(model.parameters()).device
         self.cap = edge_capacity or batch_size * 4096
-        self.ids = {k: torch.zeros((batch_size, n), dtype=torch.int64, device=dev) for k, n in zip(ID_KEYS, lens)}
-        self.rowptr = torch.zeros(batch_size * n_nodes + 1, dtype=torch.int32, device=dev)
-        self.col = torch.zeros(self.cap, dtype=torch.int32, device=dev)
-        self.val = torch.zeros(self.cap, dtype=torch.float32, device=dev)
-        self.n_global = torch.ones(1, dtype=torch.float32, device=dev)      # global token count (all ranks)
-        self.seed_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.n_global = torch.ones(1, dtype=torch.float32, device=self.dev)     # global token count (all ranks)
+        self.seed_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
         model.encoder.seed_ctr = model.decoder.seed_ctr = self.seed_ctr
         self.bucket = FlatGradBucket(model.live_parameters())
         self.optimizer = optimizer_factory(self.bucket.params)
-        self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
-        self.n_local = torch.zeros((), dtype=torch.int64, device=dev)
-        self.graph_fb = self.graph_opt = None
+        self.loss_sum = torch.zeros((), dtype=torch.float32, device=self.dev)
+        self.n_local = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self.captured = {}
+        self.cur = None
+        self.opt_ready = False
+        self.graph_opt = None
+        self.static_flat = None
 
     # ------------------------------------------------------------------ data
-    def load(self, batch):
-        """batch: [sou, tar, attr, mark, ast_change, edges, tar_label, sub_token] with `edges` a PackedEdges or a
-        host/device (rowptr, col, val) triple.  Copies into the static buffers (async when sources are pinned)."""
+    @staticmethod
+    def _split(batch):
         src = dict(zip(("sou", "tar", "attr", "mark", "ast_change", "edges", "tar_label", "sub_token"), batch))
-        for k in ID_KEYS:
-            self.ids[k].copy_(src[k], non_blocking=True)
         e = src["edges"]
-        rowptr, col, val = (e.rowptr, e.col, e.val) if isinstance(e, PackedEdges) else e
+        csr = (e.rowptr, e.col, e.val) if isinstance(e, PackedEdges) else e
+        return src, csr
+
+    def load(self, batch):
+        """batch: [sou, tar, attr, mark, ast_change, edges, tar_label, sub_token]; `edges` a PackedEdges or a
+        host/device (rowptr, col, val) triple.  Copies into the static buffers of the batch's shape
+        (async when the sources are pinned) and makes that shape current."""
+        src, (rowptr, col, val) = self._split(batch)
+        shapes = tuple(int(src[k].shape[1]) for k in ID_KEYS)
+        n_nodes = shapes[0] + shapes[3] + shapes[5]
+        if rowptr.numel() != self.B * n_nodes + 1:
+            raise ValueError("adjacency does not match the id tensors (rows != B * (n_code + n_sub + n_ast))")
         if col.numel() > self.cap:
             raise ValueError(f"batch has {col.numel()} edges, graph capacity is {self.cap}")
-        self.rowptr.copy_(rowptr, non_blocking=True)
-        self.col[:col.numel()].copy_(col, non_blocking=True)
-        self.val[:val.numel()].copy_(val, non_blocking=True)
+        c = self.captured.get(shapes)
+        if c is None:
+            c = self.captured[shapes] = _Captured(shapes, self.B, n_nodes, self.cap, self.dev)
+        for k in ID_KEYS:
+            c.ids[k].copy_(src[k], non_blocking=True)
+        c.rowptr.copy_(rowptr, non_blocking=True)
+        c.col[:col.numel()].copy_(col, non_blocking=True)
+        c.val[:val.numel()].copy_(val, non_blocking=True)
+        self.cur = c
+        return c
 
-    def _static_batch(self):
-        edges = PackedEdges(self.rowptr, self.col, self.val, self.B, self.N, True)   # fresh wrapper: no cached rowsum
-        i = self.ids
+    @staticmethod
+    def _static_batch(c, B):
+        edges = PackedEdges(c.rowptr, c.col, c.val, B, c.n_nodes, True)     # fresh wrapper: no cached rowsum
+        i = c.ids
         return [i["sou"], i["tar"], None, i["mark"], i["ast_change"], edges, i["tar_label"], i["sub_token"]]
 
     # ------------------------------------------------------------------ the step
-    def _forward_backward(self):
+    def _forward_backward(self, c):
         self.seed_ctr.add_(1)
         self.bucket.zero()
-        loss_sum, n_tok = self.model(*self._static_batch(), "train")
+        loss_sum, n_tok = self.model(*self._static_batch(c, self.B), "train")
         self.loss_sum.copy_(loss_sum.detach())
         self.n_local.copy_(n_tok)
         denom = self.n_global.squeeze(0) if self.world > 1 else n_tok.to(torch.float32)
         (loss_sum / denom).backward()
 
-    def capture(self, warmup=3):
-        """Warm up on a side stream (lazy inits, cudaFuncSetAttribute, allocator), then capture."""
+    def _count_tokens_eager(self, c):
+        if self.world > 1:
+            lab = c.ids["tar_label"]
+            self.n_global.copy_((lab[:, 1:] != 0).sum().to(torch.float32).reshape(1))
+            dist.all_reduce(self.n_global, group=self.group)
+
+    def _eager_step(self, c):
+        """A normal (uncaptured) training step: initialises the optimizer state and all lazy CUDA state."""
+        self._count_tokens_eager(c)
+        self._forward_backward(c)
+        if self.world > 1:
+            self.bucket.all_reduce(self.group)
+        self.optimizer.step()
+        self.opt_ready = True
+
+    def _capture(self, c):
+        """Warm the shape up with one forward/backward whose gradients are discarded, then capture."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._count_tokens_eager()
-                self._forward_backward()
-                self._reduce()
-                self.optimizer.step()
+            self._count_tokens_eager(c)
+            self._forward_backward(c)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.bucket.zero()
-        self.graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fb):
-            self._forward_backward()
+        c.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(c.graph):
+            self._forward_backward(c)
             if self.world == 1:
                 self.optimizer.step()
         if self.world > 1:
             # the captured backward always writes the same pool tensors; pack them into ONE static flat buffer
-            # (eager concat + NCCL all-reduce), and let the captured optimizer read views of that buffer
-            self.graph_grads = [p.grad for p in self.bucket.params]
-            self.static_flat = torch.cat([g.reshape(-1) for g in self.graph_grads])
+            # (eager concat + NCCL all-reduce) and let the captured optimizer read views of that buffer
+            c.grads = [p.grad for p in self.bucket.params]
+            if self.static_flat is None:
+                self.static_flat = torch.cat([g.reshape(-1) for g in c.grads])
             off = 0
             for p in self.bucket.params:
                 p.grad = self.static_flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt):
-                self.optimizer.step()
+            if self.graph_opt is None:
+                self.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_opt):
+                    self.optimizer.step()
+
+    def capture(self, warmup=None):
+        """Make sure the current shape is ready to replay (kept for callers that want to pay the capture
+        cost up front); performs real training steps only for the very first batch."""
+        c = self.cur
+        if not self.opt_ready:
+            self._eager_step(c)
+        if c.graph is None:
+            self._capture(c)
         return self
 
-    def _count_tokens_eager(self):
-        if self.world > 1:
-            lab = self.ids["tar_label"]
-            self.n_global.copy_((lab[:, 1:] != 0).sum().to(torch.float32).reshape(1))
-            dist.all_reduce(self.n_global, group=self.group)
-
-    def _reduce(self):
-        if self.world > 1:
-            if self.graph_fb is None:
-                self.bucket.all_reduce(self.group)                   # eager warm-up iterations
-            else:
-                torch.cat([g.reshape(-1) for g in self.graph_grads], out=self.static_flat)
-                dist.all_reduce(self.static_flat, group=self.group)
-
     def step(self, batch=None):
-        """One training step on `batch` (or on whatever is in the static buffers).  Returns the device
-        scalars (sum of the local NLL, local token count); nothing synchronises."""
-        if batch is not None:
-            self.load(batch)
-        if self.graph_fb is None:
-            self.capture()
-        self._count_tokens_eager()
-        self.graph_fb.replay()
+        """One training step on `batch` (or on what was load()ed).  Returns the device scalars (sum of the
+        local NLL, local token count); nothing synchronises once the shape's graph exists."""
+        c = self.load(batch) if batch is not None else self.cur
+        if not self.opt_ready:
+            self._eager_step(c)                       # first step of the run: eager
+            return self.loss_sum, self.n_local
+        if c.graph is None:
+            self._capture(c)
+        self._count_tokens_eager(c)
+        c.graph.replay()
         if self.world > 1:
-            self._reduce()
+            torch.cat([g.reshape(-1) for g in c.grads], out=self.static_flat)
+            dist.all_reduce(self.static_flat, group=self.group)
             self.graph_opt.replay()
         return self.loss_sum, self.n_local

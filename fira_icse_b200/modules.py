@@ -185,7 +185,8 @@ class Encoder(nn.Module):
     def forward(self, input_token, sou_mask, attr, mark, ast_change, edge, sub_token):
         # `attr` and `sou_mask` are accepted and unused, exactly like gnn_transformer.py:45
         memory = self.encode_memory(input_token, mark, ast_change, edge, sub_token)
-        return memory[:, :self.sou_len], memory[:, self.sou_len:]
+        n_code = input_token.shape[1]                 # == sou_len unless the loader trimmed the padding
+        return memory[:, :n_code], memory[:, n_code:]
 
 
 class Decoder(nn.Module):

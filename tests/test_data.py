@@ -83,3 +83,34 @@ def test_bleu_method2_known_values():
     # 'the the cat': p1 = 3/3 ('the' occurs twice in the reference), p2 = (1+1)/(2+1), p3 = p4 = (0+1)/(1+1)
     exp = math.exp(1 - 6 / 3) * math.exp(0.25 * (math.log(1.0) + math.log(2 / 3) + math.log(1 / 2) + math.log(1 / 2)))
     assert abs(bleu([ref], "the the cat".split()) - exp) < 1e-12
+
+
+def test_trim_batch_host_keeps_real_rows_and_renumbers():
+    """padding trimming: shapes shrink to the batch maximum, adjacency of real nodes and labels stay equivalent"""
+    from fira_icse_b200 import PackedEdges
+    from fira_icse_b200.data import collate_packed, trim_batch_host, build_commit
+    raw = load_raw_golden()
+    upper = set(raw["VOCAB_UPPER_CASE"])
+    V = len(raw["word_vocab"])
+    items = []
+    for i in range(6):
+        c = build_commit(raw["raw"], i, raw["word_vocab"], raw["ast_change_vocab"], upper)
+        items.append([np.array(c["sou"]), np.array(c["tar"]), None, np.array(c["mark"]), np.array(c["ast_change"]),
+                      (c["deg"], c["col"], c["val"]), np.array(c["tar_label"]), np.array(c["sub_token"])])
+    full = collate_packed(items)
+    trim = trim_batch_host(full, V)
+    c0, c1, c2 = trim[0].shape[1], trim[7].shape[1], trim[4].shape[1]
+    assert c0 < 210 and c1 < 160 and c2 < 280 and c0 % 8 == 0
+    assert torch.equal(trim[0], full[0][:, :c0]) and (full[0][:, c0:] == 0).all()
+    assert (full[7][:, c1:] == 0).all() and (full[4][:, c2:] == 0).all()
+    dense_full = PackedEdges(*full[5], 6, 650, True).to_dense()
+    dense_trim = PackedEdges(*trim[5], 6, c0 + c1 + c2, True).to_dense()
+    keep = np.r_[0:c0, 210:210 + c1, 370:370 + c2]
+    assert torch.equal(dense_trim, dense_full[:, keep][:, :, keep])
+    # removed rows were isolated self loops
+    gone = np.setdiff1d(np.arange(650), keep)
+    assert torch.equal(dense_full[:, gone][:, :, gone], torch.eye(len(gone), dtype=torch.float64).expand(6, -1, -1))
+    # labels: vocabulary and code-copy labels unchanged, sub-token copy labels shifted by the trimmed code padding
+    lf, lt = full[6], trim[6]
+    sub = lf >= V + 210
+    assert torch.equal(lt[~sub], lf[~sub]) and torch.equal(lt[sub], lf[sub] - (210 - c0))

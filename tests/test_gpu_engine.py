@@ -37,11 +37,10 @@ def test_graph_replay_equals_eager_training(precision):
     # gradient entries into full +-lr steps (the Adam graph path is covered by the test below and by bench.py)
     dp = DataParallelStep(m_eager, lambda ps: torch.optim.SGD(ps, lr=2e-3))
     eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=2e-3))
-    # capture() warms up with 3 real optimizer steps on whatever is loaded: replicate them eagerly
+    # capture() runs ONE real (eager) step on whatever is loaded before capturing: replicate it eagerly
     eng.load(batches[0])
-    eng.capture(warmup=3)
-    for _ in range(3):
-        dp.step(batches[0])
+    eng.capture()
+    dp.step(batches[0])
     tol = 5e-3 if precision == "bf16" else 2e-4
     for b in batches:
         loss_e, _ = dp.step(b)

@@ -226,3 +226,36 @@ def test_bf16_training_reduces_loss(model):
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_trimmed_batch_equals_padded_batch(model):
+    """loader-side padding trimming (data.trim_batch_host): same loss, same gradients, fewer rows"""
+    from fira_icse_b200 import PackedEdges
+    from fira_icse_b200.data import trim_batch_host
+    n = 12
+    b = golden_batch(0, n, dense_edge=False)
+    rowptr, col, val = PackedEdges.pack_host(b[5], 650)
+    full = [b[0], b[1], None, b[3], b[4], (rowptr, col, val), b[6], b[7]]
+    trim = trim_batch_host(full, model.vocab_size)
+    assert trim[0].shape[1] < 210 and trim[4].shape[1] < 280
+
+    def run(lst):
+        n_nodes = lst[0].shape[1] + lst[7].shape[1] + lst[4].shape[1]
+        dev_lst = [x.to(DEV) if torch.is_tensor(x) else x for x in lst]
+        dev_lst[5] = PackedEdges.from_host(*lst[5], n, n_nodes, DEV)
+        model.zero_grad(set_to_none=True)
+        ls, nt = model(*dev_lst, "train")
+        (ls / nt).backward()
+        with torch.no_grad():
+            ids = model(*dev_lst, "dev")
+        return ls.item(), int(nt), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}, ids
+    l_full, n_full, g_full, ids_full = run(full)
+    l_trim, n_trim, g_trim, ids_trim = run(trim)
+    assert n_full == n_trim and abs(l_full - l_trim) <= 2e-6 * abs(l_full)
+    for k in g_full:
+        scale = g_full[k].abs().max().item() + 1e-12
+        assert (g_full[k] - g_trim[k]).abs().max().item() <= 1e-4 * scale + 1e-9, k
+    # argmax ids: vocabulary and code-copy ids identical, sub-token copy ids shifted by the trimmed code padding
+    V, c0 = model.vocab_size, trim[0].shape[1]
+    expect = torch.where(ids_full >= V + 210, ids_full - (210 - c0), ids_full)
+    assert torch.equal(ids_trim, expect)
