@@ -375,6 +375,9 @@ def run_gpu_arm(args):
         eng = GraphedTrainStep(model, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True))
         eng.load(pool_dev[0])
         eng.capture()                                                # one eager step + capture of this shape
+        for hb in pool_dev[1:]:                                      # trimmed batches come in a few shapes:
+            eng.step(hb)                                             # capture each shape's graph before timing
+        eng.load(pool_dev[0])
         c0 = _lib.LAUNCH_COUNT
         eng._forward_backward(eng.cur)                               # count the C-ABI calls of one step (eager)
         launches_per_step = _lib.LAUNCH_COUNT - c0

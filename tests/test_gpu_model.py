@@ -253,7 +253,9 @@ def test_trimmed_batch_equals_padded_batch(model):
     l_trim, n_trim, g_trim, ids_trim = run(trim)
     assert n_full == n_trim and abs(l_full - l_trim) <= 2e-6 * abs(l_full)
     for k in g_full:
-        scale = g_full[k].abs().max().item() + 1e-12
+        scale = g_full[k].abs().max().item()
+        if scale < 1e-6:          # shift-invariant biases: exactly zero in exact arithmetic, round-off noise here
+            continue
         assert (g_full[k] - g_trim[k]).abs().max().item() <= 1e-4 * scale + 1e-9, k
     # argmax ids: vocabulary and code-copy ids identical, sub-token copy ids shifted by the trimmed code padding
     V, c0 = model.vocab_size, trim[0].shape[1]
