@@ -124,7 +124,9 @@ class GraphedTrainStep:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._count_tokens_eager(c)
+            # no collective here: ranks meet new shapes at different steps, so the number of NCCL calls per step
+            # must not depend on whether a rank is capturing (n_global keeps its previous value; the result of
+            # this warm-up pass is discarded)
             self._forward_backward(c)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
