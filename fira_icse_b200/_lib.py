@@ -77,3 +77,8 @@ def call(name, *args):
     global LAUNCH_COUNT
     LAUNCH_COUNT += 1
     check(getattr(lib(), name)(*args), name)
+
+
+def host_call(name, *args):
+    """C-ABI entry points that run on the host (fira_host_*): not counted as GPU launches."""
+    check(getattr(lib(), name)(*args), name)

@@ -13,13 +13,14 @@ what changes is the representation handed to the model:
 reference's own DataLoader/collate keeps working.
 """
 import json
-import math
 import os
 import random
 
 import numpy as np
 import torch
 from torch.utils.data import Dataset
+
+from ._lib import host_call
 
 num_train, num_valid, num_test = 75000, 8000, 7661          # Dataset.py:10-12
 lemmatization = {"added": "add", "fixed": "fix", "removed": "remove",
@@ -44,6 +45,30 @@ def _fit(seq, n):
     return (list(seq) + [0] * n)[:n]
 
 
+def _pairs(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32).reshape(-1, 2))
+
+
+def build_adjacency(change_code, change_ast, ast_code, ast_ast, code_sub, n_diff, n_ast, diff_len=210, sub_len=160,
+                    ast_change_len=280):
+    """Commit graph of Dataset.py:220-294,346-357 through the native builder (fira_host_build_adjacency):
+    relation pair lists as stored in DataSet/edge_*.json -> (deg int32[n_nodes], col int32[nnz], val f64[nnz])
+    in CSR order; undirected, de-duplicated, self loop on every node, value 1/sqrt(deg_r)/sqrt(deg_c)."""
+    rel = [_pairs(r) for r in (change_code, change_ast, ast_code, ast_ast, code_sub)]
+    n_nodes = diff_len + sub_len + ast_change_len
+    cap = 2 * (sum(len(r) for r in rel) + n_diff + 1) + n_nodes
+    deg = np.empty(n_nodes, np.int32)
+    col = np.empty(cap, np.int32)
+    val = np.empty(cap, np.float64)
+    nnz = np.zeros(1, np.int32)
+    args = []
+    for r in rel:
+        args += [r.ctypes.data, len(r)]
+    host_call("fira_host_build_adjacency", *args, int(n_diff), int(n_ast), diff_len, sub_len, ast_change_len,
+              deg.ctypes.data, col.ctypes.data, val.ctypes.data, cap, nnz.ctypes.data)
+    return deg, col[:nnz[0]].copy(), val[:nnz[0]].copy()
+
+
 def build_commit(raw, i, vocab, ast_vocab, upper, diff_len=210, msg_len=30, att_len=25, ast_change_len=280,
                  sub_len=160):
     """One commit -> padded id arrays + CSR pieces of its normalised adjacency.
@@ -58,7 +83,6 @@ def build_commit(raw, i, vocab, ast_vocab, upper, diff_len=210, msg_len=30, att_
     atts = raw["diffatt"][i]
     V = len(vocab)
     n_ast = len(raw["ast"][i])
-    n_nodes = diff_len + sub_len + ast_change_len
 
     sou = _fit([vocab["<start>"]] + _to_ids(diff, vocab, upper) + [vocab["<eos>"]], diff_len)
     msg_ids = _to_ids(msg, vocab, upper)
@@ -92,23 +116,10 @@ def build_commit(raw, i, vocab, ast_vocab, upper, diff_len=210, msg_len=30, att_
             label.append(wid)
     tar_label = _fit([vocab["<start>"]] + label + [vocab["<eos>"]], msg_len)
 
-    # adjacency as a set of ordered pairs, keyed r*n + c
-    a0 = diff_len + sub_len
-    und = []
-    und += [(c + a0 + n_ast, j + 1) for c, j in raw["edge_change_code"][i] if j + 1 < diff_len]
-    und += [(c + a0 + n_ast, a + a0) for c, a in raw["edge_change_ast"][i]]
-    und += [(a + a0, j + 1) for a, j in raw["edge_ast_code"][i] if j + 1 < diff_len]
-    und += [(a + a0, b + a0) for a, b in raw["edge_ast"][i]]
-    und += [(j + 1, k + diff_len) for j, k in code_sub]
-    und += [(j, j + 1) for j in range(len(diff) + 1)]
-    e = np.array(und, np.int64).reshape(-1, 2)
-    assert (e[:, 0] != e[:, 1]).all(), "the DataSet has no self edges (Dataset.py:275)"
-    keys = np.unique(np.concatenate((e[:, 0] * n_nodes + e[:, 1], e[:, 1] * n_nodes + e[:, 0],
-                                     np.arange(n_nodes) * (n_nodes + 1))))
-    row, col = keys // n_nodes, keys % n_nodes
-    deg_r = np.bincount(row, minlength=n_nodes)
-    deg_c = np.bincount(col, minlength=n_nodes)
-    val = np.array([1 / math.sqrt(deg_r[r]) / math.sqrt(deg_c[c]) for r, c in zip(row, col)], np.float64)
+    deg_r, col, val = build_adjacency(raw["edge_change_code"][i], raw["edge_change_ast"][i], raw["edge_ast_code"][i],
+                                      raw["edge_ast"][i], code_sub, len(diff), n_ast, diff_len, sub_len, ast_change_len)
+    if deg_r.max() > 255:
+        raise ValueError("a node has more than 255 neighbours: the packed degree table is uint8")
     attr_pos = [j + 1 for j, att in enumerate(atts) if att]           # row of the padded [210,25] attr matrix
     attr_ids = [_fit(_to_ids(atts[j - 1], vocab, upper), att_len) for j in attr_pos]
     return dict(sou=sou, tar=tar, mark=mark, ast_change=ast_change, tar_label=tar_label, sub_token=sub_token,
@@ -245,7 +256,8 @@ def trim_batch_host(batch, vocab_size, multiple=8, full=(210, 160, 280)):
     B = sou.shape[0]
 
     def cap(t, n):
-        used = int((t != 0).sum(1).max()) if t.numel() else 0
+        nz = (t != 0).any(0).nonzero()
+        used = int(nz.max()) + 1 if nz.numel() else 0            # position after the last non-padding id
         return min(n, max(multiple, -(-used // multiple) * multiple))
     c0, c1, c2 = cap(sou, n0), cap(sub_token, n1), cap(ast_change, n2)
     N, Nt = n0 + n1 + n2, c0 + c1 + c2
@@ -267,3 +279,151 @@ def trim_batch_host(batch, vocab_size, multiple=8, full=(210, 160, 280)):
            (torch.from_numpy(new_rowptr.astype(np.int32)), torch.from_numpy(new_col.astype(np.int32)),
             torch.from_numpy(val.numpy()[entry_keep])), label, sub_token[:, :c1].contiguous()]
     return out
+
+
+class _Slot:
+    """One set of staging buffers (pinned when CUDA is present) sized for an untrimmed batch."""
+
+    def __init__(self, B, lens, msg_len, edge_cap, pin):
+        n0, n1, n2 = lens
+
+        def buf(n, dt):
+            t = torch.empty(n, dtype=dt)
+            return t.pin_memory() if pin else t
+        self.sou, self.mark = buf(B * n0, torch.int64), buf(B * n0, torch.int64)
+        self.sub_token, self.ast_change = buf(B * n1, torch.int64), buf(B * n2, torch.int64)
+        self.tar, self.tar_label = buf(B * msg_len, torch.int64), buf(B * msg_len, torch.int64)
+        self.rowptr = buf(B * (n0 + n1 + n2) + 1, torch.int32)
+        self.col, self.val = buf(edge_cap, torch.int32), buf(edge_cap, torch.float32)
+        self.event = None
+        self.batch = None
+
+
+class PackedBatchLoader:
+    """Native loader for a TransDataset: every batch is gathered, collated, padding-trimmed and CSR-packed by ONE
+    call of fira_host_gather_batch (C++) into pinned staging buffers, on a background thread, `prefetch` batches
+    ahead of the consumer.  Replaces DataLoader(dataset, collate_fn=...) + trim_batch_host.
+
+    Yields the reference's 8-slot batch [sou, tar, None, mark, ast_change, (rowptr, col, val), tar_label,
+    sub_token] as HOST tensors that are views of a staging slot: the consumer must enqueue its host->device
+    copies (GraphedTrainStep.step / batch_to_device) before asking for the next batch -- the slot is recycled
+    only after a CUDA event recorded at that moment has completed.
+
+    multiples: rounding of the trimmed (code, sub-token, AST) segment lengths; None = no trimming.
+    max_shapes: upper bound on the number of distinct batch shapes ever emitted (each shape is one captured
+    CUDA graph downstream); once reached, a batch is padded up to the smallest already-emitted shape that
+    holds it (the full 210/160/280 if none does)."""
+
+    def __init__(self, dataset, batch_size, vocab_size, shuffle=False, indices=None, multiples=(8, 8, 8),
+                 max_shapes=None, drop_last=False, prefetch=2, pin=None):
+        self.ds, self.B, self.V = dataset, int(batch_size), int(vocab_size)
+        self.shuffle, self.drop_last = shuffle, drop_last
+        self.indices = np.arange(len(dataset), dtype=np.int64) if indices is None else np.asarray(indices, np.int64)
+        self.multiples = (0, 0, 0) if multiples is None else tuple(int(m) for m in multiples)
+        self.max_shapes = max_shapes
+        self.shapes = {}
+        self.lens = (dataset.diff_len, dataset.sub_token_len, dataset.ast_change_len)
+        self.msg_len = dataset.msg_len
+        d = dataset.d
+        self.tab = {k: np.ascontiguousarray(d[k], dtype=np.int32) for k in TransDataset.ID_KEYS}
+        self.deg = np.ascontiguousarray(d["deg"], dtype=np.uint8)
+        self.col = np.ascontiguousarray(d["col"], dtype=np.int16)
+        self.val = np.ascontiguousarray(d["val"], dtype=np.float64)
+        self.edge_ptr = np.ascontiguousarray(d["edge_ptr"], dtype=np.int64)
+        per_commit = int(np.diff(self.edge_ptr).max()) if len(self.edge_ptr) > 1 else 0
+        self.edge_cap = max(1, per_commit * self.B)
+        self.pin = torch.cuda.is_available() if pin is None else pin
+        self.n_slots = max(2, int(prefetch) + 1)
+        self.slots = [_Slot(self.B, self.lens, self.msg_len, self.edge_cap, self.pin) for _ in range(self.n_slots)]
+
+    def __len__(self):
+        n = len(self.indices)
+        return n // self.B if self.drop_last else -(-n // self.B)
+
+    # ------------------------------------------------------------------ shape policy
+    def _choose_dims(self, need):
+        need = tuple(int(x) for x in need)
+        if need in self.shapes or self.max_shapes is None or len(self.shapes) < self.max_shapes:
+            self.shapes[need] = self.shapes.get(need, 0) + 1
+            return need
+        fits = [s for s in self.shapes if all(a >= b for a, b in zip(s, need))]
+        best = min(fits, key=sum) if fits else self.lens
+        self.shapes[best] = self.shapes.get(best, 0) + 1
+        return best
+
+    # ------------------------------------------------------------------ one batch
+    def gather(self, index, slot=None):
+        """index: int64 dataset positions -> batch (views of `slot`)."""
+        slot = self.slots[0] if slot is None else slot
+        index = np.ascontiguousarray(index, dtype=np.int64)
+        b = len(index)
+        n0, n1, n2 = self.lens
+        t = self.tab
+        dims = np.zeros(3, np.int32)
+        host_call("fira_host_batch_dims", t["sou"].ctypes.data, t["sub_token"].ctypes.data,
+                  t["ast_change"].ctypes.data, index.ctypes.data, b, n0, n1, n2, *self.multiples, dims.ctypes.data)
+        dims = np.asarray(self._choose_dims(dims), np.int32)
+        nnz = np.zeros(1, np.int32)
+        host_call("fira_host_gather_batch", t["sou"].ctypes.data, t["tar"].ctypes.data, t["mark"].ctypes.data,
+                  t["ast_change"].ctypes.data, t["tar_label"].ctypes.data, t["sub_token"].ctypes.data,
+                  self.deg.ctypes.data, self.col.ctypes.data, self.val.ctypes.data, self.edge_ptr.ctypes.data,
+                  index.ctypes.data, b, n0, n1, n2, self.msg_len, self.V, dims.ctypes.data,
+                  slot.sou.data_ptr(), slot.tar.data_ptr(), slot.mark.data_ptr(), slot.ast_change.data_ptr(),
+                  slot.tar_label.data_ptr(), slot.sub_token.data_ptr(), slot.rowptr.data_ptr(), slot.col.data_ptr(),
+                  slot.val.data_ptr(), self.edge_cap, nnz.ctypes.data)
+        c0, c1, c2 = (int(x) for x in dims)
+        e = int(nnz[0])
+        slot.batch = [slot.sou[:b * c0].view(b, c0), slot.tar[:b * self.msg_len].view(b, self.msg_len), None,
+                      slot.mark[:b * c0].view(b, c0), slot.ast_change[:b * c2].view(b, c2),
+                      (slot.rowptr[:b * (c0 + c1 + c2) + 1], slot.col[:e], slot.val[:e]),
+                      slot.tar_label[:b * self.msg_len].view(b, self.msg_len), slot.sub_token[:b * c1].view(b, c1)]
+        return slot.batch
+
+    # ------------------------------------------------------------------ iteration
+    def __iter__(self):
+        import queue
+        import threading
+        order = self.indices
+        if self.shuffle:
+            order = order[torch.randperm(len(order)).numpy()]        # torch's global generator, like DataLoader
+        chunks = [order[i:i + self.B] for i in range(0, len(order), self.B)]
+        if self.drop_last and chunks and len(chunks[-1]) < self.B:
+            chunks.pop()
+        free_q, full_q = queue.Queue(), queue.Queue()
+        for s in self.slots:
+            s.event = None
+            free_q.put(s)
+        stop = threading.Event()
+
+        def produce():
+            try:
+                for ch in chunks:
+                    s = free_q.get()
+                    if stop.is_set():
+                        return
+                    if s.event is not None:
+                        s.event.synchronize()                # the consumer's copies out of this slot have run
+                    self.gather(ch, s)
+                    full_q.put(s)
+                full_q.put(None)
+            except BaseException as exc:                      # surface loader errors in the consumer
+                full_q.put(exc)
+
+        th = threading.Thread(target=produce, daemon=True)
+        th.start()
+        try:
+            while True:
+                s = full_q.get()
+                if s is None:
+                    break
+                if isinstance(s, BaseException):
+                    raise s
+                yield s.batch
+                if self.pin:
+                    s.event = torch.cuda.Event()
+                    s.event.record()
+                free_q.put(s)
+        finally:
+            stop.set()
+            free_q.put(self.slots[0])
+            th.join(timeout=5)

@@ -146,6 +146,45 @@ int fira_pointer_mix_nll_bwd(const void* logits, long ld_logits, const float* co
                              const float* upstream, void* d_logits, float* d_copy_scores, float* d_gate_logits,
                              unsigned char* row_active, long rows, int T_len, int V, int S, int dtype, void* stream);
 
+/* ---- HOST-side batch preparation (CPU only: every pointer below is HOST memory, there is no stream).
+ *
+ * fira_host_build_adjacency: the commit graph of Dataset.py:220-294 + process_edge (Dataset.py:346-357).
+ *   Relations are int32 pair lists [n,2] exactly as stored in DataSet/edge_*.json: (edit c, code j),
+ *   (edit c, AST a), (AST a, code j), (AST a, AST b); code_sub = (code j, sub-token k) pairs
+ *   (Dataset.py:173-192, 255-259); n_diff = diff tokens before padding (the sequential chain covers
+ *   <start> t1..tn <eos>, Dataset.py:263-266); n_ast = AST nodes (edit nodes follow them).
+ *   Node ids: code j -> j+1, sub-token k -> diff_len+k, AST a -> diff_len+sub_len+a, edit c -> ...+n_ast+c;
+ *   pairs whose code id reaches diff_len are dropped (Dataset.py:228,243).  Output: undirected,
+ *   de-duplicated, self loop on every node, in CSR order: deg[n_nodes], col[nnz], val[nnz] =
+ *   1/sqrt(deg_row)/sqrt(deg_col) in float64 (Dataset.py:277-291).  *nnz_out is set even when cap is
+ *   too small (FIRA_ERR_SHAPE).
+ *
+ * fira_host_batch_dims: segment lengths a batch needs after dropping the padding ALL its commits share:
+ *   dims[3] = {c0, c1, c2} = position after the last non-zero id over commits index[0..batch) of the
+ *   code / sub-token / AST+edit id tables, rounded up to mult_* (mult <= 0: keep the full length).
+ *
+ * fira_host_gather_batch: the loader step (Dataset.py:336-343 __getitem__ + default collate, minus the dense
+ *   float64 toarray()): gathers commits index[0..batch) from the packed split arrays (int32 id tables
+ *   [n, len], deg uint8 [n, n_nodes], col int16 / val float64 concatenated, edge_ptr int64 [n+1]) into
+ *   caller-owned staging buffers (pinned memory): int64 id tensors [batch, c*] written with row length
+ *   dims[0..2] (from fira_host_batch_dims, or any larger lengths up to the full 210/160/280), batch CSR
+ *   rowptr int32 [batch*(c0+c1+c2)+1], col int32, val fp32.  The nodes cut away are isolated self loops
+ *   (Dataset.py:271-275); sub-token copy labels (Dataset.py:213) shift by the removed code padding.
+ *   Fails if a commit has a real id or a neighbour beyond dims. */
+int fira_host_build_adjacency(const int* change_code, int n_change_code, const int* change_ast, int n_change_ast,
+                              const int* ast_code, int n_ast_code, const int* ast_ast, int n_ast_ast,
+                              const int* code_sub, int n_code_sub, int n_diff, int n_ast, int diff_len, int sub_len,
+                              int ast_change_len, int* deg, int* col, double* val, int cap, int* nnz_out);
+int fira_host_batch_dims(const int* sou, const int* sub_token, const int* ast_change, const long* index, int batch,
+                         int diff_len, int sub_len, int ast_change_len, int mult_code, int mult_sub, int mult_ast,
+                         int* dims);
+int fira_host_gather_batch(const int* sou, const int* tar, const int* mark, const int* ast_change,
+                           const int* tar_label, const int* sub_token, const unsigned char* deg, const short* col,
+                           const double* val, const long* edge_ptr, const long* index, int batch, int diff_len,
+                           int sub_len, int ast_change_len, int msg_len, int vocab_size, const int* dims,
+                           long* o_sou, long* o_tar, long* o_mark, long* o_ast_change, long* o_tar_label,
+                           long* o_sub_token, int* o_rowptr, int* o_col, float* o_val, long edge_cap, int* nnz_out);
+
 #ifdef __cplusplus
 }
 #endif

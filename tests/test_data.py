@@ -85,6 +85,76 @@ def test_bleu_method2_known_values():
     assert abs(bleu([ref], "the the cat".split()) - exp) < 1e-12
 
 
+def test_native_adjacency_equals_oracle_builder_and_rejects_bad_input():
+    """fira_host_build_adjacency (C++) against the pure-Python restatement of Dataset.py in oracle/graph_oracle.py
+    (the comparison with the reference's own output is test_build_commit_equals_reference_process_data)."""
+    import graph_oracle as G
+    from fira_icse_b200._lib import FiraLibraryError
+    from fira_icse_b200.data import build_adjacency, build_commit
+    raw = load_raw_golden()
+    upper = set(raw["VOCAB_UPPER_CASE"])
+    for i in (0, 7, 63, 127):
+        mine = build_commit(raw["raw"], i, raw["word_vocab"], raw["ast_change_vocab"], upper)
+        ref = G.build_commit(raw["raw"], i, raw["word_vocab"], raw["ast_change_vocab"], raw["VOCAB_UPPER_CASE"])
+        dense = np.zeros((650, 650)); dense[np.repeat(np.arange(650), mine["deg"]), mine["col"]] = mine["val"]
+        want = np.zeros((650, 650)); want[ref["row"], ref["col"]] = ref["val"]
+        assert np.array_equal(dense, want), i                   # float64 values bit-identical
+        assert mine["deg"].sum() == len(mine["col"]) == len(mine["val"]) == len(ref["val"])
+    # tiny hand-checked graph: code chain <start>-t1-<eos> (n_diff = 1) + one AST node tied to t1
+    deg, col, val = build_adjacency([], [], [(0, 0)], [], [], n_diff=1, n_ast=1, diff_len=4, sub_len=2, ast_change_len=2)
+    assert deg.tolist() == [2, 4, 2, 1, 1, 1, 2, 1]            # node 6 = first AST node, tied to code node 1
+    assert col.tolist() == [0, 1, 0, 1, 2, 6, 1, 2, 3, 4, 5, 1, 6, 7]
+    import math
+    assert val[0] == 1 / math.sqrt(2) / math.sqrt(2) and val[1] == 1 / math.sqrt(2) / math.sqrt(4) and val[-1] == 1.0
+    with pytest.raises(FiraLibraryError):                       # AST id outside the padded graph
+        build_adjacency([], [], [], [(0, 5)], [], n_diff=1, n_ast=1, diff_len=4, sub_len=2, ast_change_len=2)
+    with pytest.raises(FiraLibraryError):                       # self edge
+        build_adjacency([], [], [], [(1, 1)], [], n_diff=1, n_ast=2, diff_len=4, sub_len=2, ast_change_len=2)
+    # edges to code tokens beyond the padded diff are dropped, not an error (Dataset.py:228,243)
+    deg2, _, _ = build_adjacency([], [], [(0, 3)], [], [], n_diff=1, n_ast=1, diff_len=4, sub_len=2, ast_change_len=2)
+    assert deg2.tolist() == [2, 3, 2, 1, 1, 1, 1, 1]
+
+
+def test_native_loader_equals_python_collate_and_trim(tmp_path):
+    """PackedBatchLoader (fira_host_batch_dims + fira_host_gather_batch) == collate_packed + trim_batch_host."""
+    from fira_icse_b200.data import PackedBatchLoader, TransDataset, collate_packed, trim_batch_host
+    raw = load_raw_golden()
+    _write_dataset(str(tmp_path), raw, n=60)
+    ds = TransDataset(reference_args(), "train", root=str(tmp_path))
+    V = len(raw["word_vocab"])
+    n = len(ds)
+    ld = PackedBatchLoader(ds, 8, V, shuffle=False, multiples=(8, 8, 8), pin=False)
+    assert len(ld) == -(-n // 8)
+    seen = 0
+    for k, got in enumerate(ld):
+        idx = list(range(k * 8, min(n, k * 8 + 8)))
+        want = trim_batch_host(collate_packed([ds[i] for i in idx]), V)
+        for j in (0, 1, 3, 4, 6, 7):
+            assert got[j].dtype == torch.int64 and torch.equal(got[j], want[j]), (k, j)
+        assert got[2] is None
+        for a, b in zip(got[5], want[5]):
+            assert a.dtype == b.dtype and torch.equal(a, b), k
+        seen += len(idx)
+    assert seen == n
+    # untrimmed mode reproduces collate_packed itself
+    full = PackedBatchLoader(ds, 5, V, multiples=None, pin=False).gather(np.arange(5))
+    want = collate_packed([ds[i] for i in range(5)])
+    assert all(torch.equal(full[j], want[j]) for j in (0, 1, 3, 4, 6, 7))
+    assert all(torch.equal(a, b) for a, b in zip(full[5], want[5]))
+    # shape budget: with one allowed shape every later batch is padded up to a shape that holds it
+    capped = PackedBatchLoader(ds, 8, V, multiples=(8, 8, 8), max_shapes=1, pin=False)
+    shapes = [(b[0].shape[1], b[7].shape[1], b[4].shape[1]) for b in capped]
+    assert len(set(shapes)) <= 2 and all(s == shapes[0] or s == (210, 160, 280) for s in shapes)
+    # shuffled epochs are permutations driven by torch's generator
+    torch.manual_seed(3)
+    sh = PackedBatchLoader(ds, 8, V, shuffle=True, pin=False)
+    first = torch.cat([b[1] for b in sh])
+    torch.manual_seed(3)
+    again = torch.cat([b[1] for b in sh])
+    assert torch.equal(first, again) and first.shape[0] == n
+    assert not torch.equal(first, torch.cat([b[1] for b in ld]))
+
+
 def test_trim_batch_host_keeps_real_rows_and_renumbers():
     """padding trimming: shapes shrink to the batch maximum, adjacency of real nodes and labels stay equivalent"""
     from fira_icse_b200 import PackedEdges
