@@ -12,11 +12,17 @@ What makes the path capturable
     so replays draw fresh masks although the host-side seed is frozen into the graph;
   * TMA tensor maps are kernel parameters, rebuilt at capture time for the pooled buffers;
   * weight-gradient work and weight preparation run on a forked stream = parallel graph branches.
-Batches whose padding was trimmed by the loader (data.trim_batch_host) come in a few distinct
-(n_code, n_sub, n_ast) shapes: one graph per shape, one shared optimizer.
+Batches whose padding was trimmed by the loader (data.PackedBatchLoader / trim_batch_host) come in a few
+distinct (batch, n_code, n_sub, n_ast) shapes: one graph per shape, one shared optimizer.  The graphs are
+replayed strictly one after the other on one stream and nothing produced inside one is read after the
+next has started (losses are copied to static scalars inside the graph, gradients are consumed by the
+optimizer inside the graph or right after the replay), so all of them capture into ONE memory pool: device
+memory is the maximum over the shapes, not the sum (FIRA_GRAPH_PRIVATE_POOLS=1 gives each graph its own).
 N > 1: forward/backward graph, eager NCCL all-reduce of ONE flat gradient buffer, optimizer graph
 (same numerics as parallel.DataParallelStep).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -34,14 +40,14 @@ class _Captured:
         self.rowptr = torch.zeros(B * n_nodes + 1, dtype=torch.int32, device=dev)
         self.col = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.val = torch.zeros(cap, dtype=torch.float32, device=dev)
-        self.n_nodes, self.cap = n_nodes, cap
+        self.B, self.n_nodes, self.cap = B, n_nodes, cap
         self.graph = None
         self.grads = None
 
 
 class GraphedTrainStep:
     def __init__(self, model, batch_size, optimizer_factory, edge_capacity=None, group=None):
-        self.model, self.B, self.group = model, batch_size, group
+        self.model, self.B, self.group = model, batch_size, group          # B: the largest batch (sizes the CSR capacity)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.dev = next(model.parameters()).device
         self.cap = edge_capacity or batch_size * 4096
@@ -57,6 +63,7 @@ class GraphedTrainStep:
         self.opt_ready = False
         self.graph_opt = None
         self.static_flat = None
+        self.pool = None                     # graph memory pool shared by every captured shape
 
     # ------------------------------------------------------------------ data
     @staticmethod
@@ -72,14 +79,15 @@ class GraphedTrainStep:
         (async when the sources are pinned) and makes that shape current."""
         src, (rowptr, col, val) = self._split(batch)
         shapes = tuple(int(src[k].shape[1]) for k in ID_KEYS)
+        B = int(src["sou"].shape[0])
         n_nodes = shapes[0] + shapes[3] + shapes[5]
-        if rowptr.numel() != self.B * n_nodes + 1:
+        if rowptr.numel() != B * n_nodes + 1:
             raise ValueError("adjacency does not match the id tensors (rows != B * (n_code + n_sub + n_ast))")
         if col.numel() > self.cap:
             raise ValueError(f"batch has {col.numel()} edges, graph capacity is {self.cap}")
-        c = self.captured.get(shapes)
-        if c is None:
-            c = self.captured[shapes] = _Captured(shapes, self.B, n_nodes, self.cap, self.dev)
+        c = self.captured.get((B,) + shapes)
+        if c is None:               # a new (batch, n_code, n_sub, n_ast) shape, e.g. the short last batch of an epoch
+            c = self.captured[(B,) + shapes] = _Captured(shapes, B, n_nodes, self.cap, self.dev)
         for k in ID_KEYS:
             c.ids[k].copy_(src[k], non_blocking=True)
         c.rowptr.copy_(rowptr, non_blocking=True)
@@ -98,7 +106,7 @@ class GraphedTrainStep:
     def _forward_backward(self, c):
         self.seed_ctr.add_(1)
         self.bucket.zero()
-        loss_sum, n_tok = self.model(*self._static_batch(c, self.B), "train")
+        loss_sum, n_tok = self.model(*self._static_batch(c, c.B), "train")
         self.loss_sum.copy_(loss_sum.detach())
         self.n_local.copy_(n_tok)
         denom = self.n_global.squeeze(0) if self.world > 1 else n_tok.to(torch.float32)
@@ -131,8 +139,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.bucket.zero()
+        if self.pool is None and os.environ.get("FIRA_GRAPH_PRIVATE_POOLS", "0") != "1":
+            self.pool = torch.cuda.graph_pool_handle()
         c.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(c.graph):
+        with torch.cuda.graph(c.graph, pool=self.pool):
             self._forward_backward(c)
             if self.world == 1:
                 self.optimizer.step()
@@ -148,7 +158,7 @@ class GraphedTrainStep:
                 off += p.numel()
             if self.graph_opt is None:
                 self.graph_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph_opt):
+                with torch.cuda.graph(self.graph_opt):        # private pool: Adam's temporaries live across shapes
                     self.optimizer.step()
 
     def capture(self, warmup=None):

@@ -8,9 +8,13 @@ epoch 15, best checkpoint saved as a plain state_dict with the reference's 338 k
 beam search ranking.  Differences, all below the module surface:
   * one process per GPU (launch with torchrun for N > 1) with an NCCL gradient all-reduce instead of
     nn.DataParallel; batch 170 PER GPU like upstream (run_model.py:40);
-  * the loader emits packed CSR adjacency from pinned memory instead of dense float64 650x650;
+  * training batches come from the native loader (data.PackedBatchLoader: C++ gather + padding trim + CSR
+    packing into pinned memory) instead of dense float64 650x650 through DataLoader workers;
+  * the training step (zero-grad, forward, backward, Adam) is replayed as a CUDA graph per batch shape
+    (engine.GraphedTrainStep); FIRA_ENGINE=eager issues the same kernels launch by launch;
   * optional env overrides, defaults unchanged: FIRA_BATCH, FIRA_TEST_BATCH, FIRA_EPOCHS, FIRA_BEAM,
-    FIRA_MAX_BATCHES (smoke runs), FIRA_WORKERS.
+    FIRA_MAX_BATCHES (smoke runs), FIRA_WORKERS, FIRA_PRECISION (fp32 parity mode | bf16 throughput mode),
+    FIRA_MAX_SHAPES (bound on distinct trimmed batch shapes = captured graphs, default 24).
 """
 import json
 import os
@@ -26,7 +30,8 @@ from torch.utils.data import DataLoader
 from fira_icse_b200 import TransModel
 from fira_icse_b200.beam import beam_search, best_sequences
 from fira_icse_b200.bleu import sentence_bleu_method2
-from fira_icse_b200.data import TransDataset, batch_to_device, collate_packed
+from fira_icse_b200.data import PackedBatchLoader, TransDataset, batch_to_device, collate_packed
+from fira_icse_b200.engine import GraphedTrainStep
 from fira_icse_b200.parallel import DataParallelStep, shard_range
 
 
@@ -128,7 +133,8 @@ def dev(model, dev_loader, g, valid_index, epoch, dev):
 
 def train_epoch(dp, model, train_loader, epoch, best_bleu, dev_loader, g, valid_index, dev_):
     model.train()
-    total_data, total_loss = 0, 0.0
+    graphed = isinstance(dp, GraphedTrainStep)
+    total_data, total_loss = 0, (torch.zeros((), device=dev_) if graphed else 0.0)
     max_batches = int(os.environ.get("FIRA_MAX_BATCHES", 0))
     for idx, batch in enumerate(train_loader):
         if max_batches and idx >= max_batches:
@@ -145,14 +151,22 @@ def train_epoch(dp, model, train_loader, epoch, best_bleu, dev_loader, g, valid_
             if WORLD > 1:
                 dist.barrier()
             model.train()
-        loss, _ = dp.step(batch_to_device(batch, dev_))
+        if graphed:
+            loss_sum, n_tok = dp.step(batch)              # pinned host batch -> static buffers -> graph replay
+            total_loss += loss_sum / n_tok                # stays on the device: no sync per step
+        else:
+            loss, _ = dp.step(batch_to_device(batch, dev_))
+            total_loss += loss.item()
         total_data += len(batch[0]) * WORLD
-        total_loss += loss.item()
         if idx % 10 == 0 and RANK == 0:
             print("epoch: %d batch: %d/%d  data: %d/%d loss: %.4f" % (
-                epoch, idx, len(train_loader), total_data, len(train_loader.dataset) * WORLD, total_loss / 10))
-            total_loss = 0
+                epoch, idx, len(train_loader), total_data, n_train_total(train_loader) * WORLD, float(total_loss) / 10))
+            total_loss = torch.zeros((), device=dev_) if graphed else 0.0
     return best_bleu
+
+
+def n_train_total(train_loader):
+    return len(train_loader.indices) if isinstance(train_loader, PackedBatchLoader) else len(train_loader.dataset)
 
 
 def main_train():
@@ -166,10 +180,17 @@ def main_train():
     lo, hi = shard_range(len(train_set), RANK, WORLD)               # graphs shard by commit
     if WORLD > 1:
         hi = lo + (len(train_set) // WORLD)                         # equal step counts on every rank
-    train_loader = loader(train_set, args.batch_size, True, list(range(lo, hi)) if WORLD > 1 else None)
     dev_loader = loader(dev_set, args.batch_size, False)
     model = TransModel(args).to(dev_)
-    dp = DataParallelStep(model, lambda ps: Adam(ps, args.lr, fused=True))
+    if os.environ.get("FIRA_ENGINE", "graph") == "graph":
+        train_loader = PackedBatchLoader(train_set, args.batch_size, args.vocab_size, shuffle=True,
+                                         indices=range(lo, hi) if WORLD > 1 else None, multiples=(8, 16, 16),
+                                         max_shapes=int(os.environ.get("FIRA_MAX_SHAPES", 24)), drop_last=WORLD > 1)
+        dp = GraphedTrainStep(model, args.batch_size, lambda ps: Adam(ps, args.lr, fused=True, capturable=True),
+                              edge_capacity=train_loader.edge_cap)
+    else:
+        train_loader = loader(train_set, args.batch_size, True, list(range(lo, hi)) if WORLD > 1 else None)
+        dp = DataParallelStep(model, lambda ps: Adam(ps, args.lr, fused=True))
     best_bleu = -1
     for epoch in range(args.epoches):
         best_bleu = train_epoch(dp, model, train_loader, epoch, best_bleu, dev_loader, g, all_index['valid'], dev_)

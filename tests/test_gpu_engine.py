@@ -69,3 +69,42 @@ def test_graph_replays_draw_fresh_dropout_masks():
     assert int(eng.seed_ctr.item()) == c0 + 4
     assert len({round(x, 6) for x in losses}) == 4, losses      # lr = 0: only the masks differ
     assert np.std(losses) < 0.05 * np.mean(losses)
+
+
+def test_multi_shape_graphs_share_one_pool_and_match_eager():
+    """Trimmed batches of different (batch, n_code, n_sub, n_ast) shapes: one graph per shape captured into a
+    shared memory pool, replayed in arbitrary order, must train exactly like the eager step."""
+    from fira_icse_b200 import PackedEdges
+    from fira_icse_b200.data import trim_batch_host
+    from fira_icse_b200.engine import GraphedTrainStep
+    from fira_icse_b200.parallel import DataParallelStep
+    base = copy.deepcopy(seeded_model()).to(DEV)
+    base.eval()
+    m_eager, m_graph = copy.deepcopy(base), copy.deepcopy(base)
+
+    def host(lo, hi):
+        b = golden_batch(lo, hi, dense_edge=False)
+        full = [b[0], b[1], None, b[3], b[4], PackedEdges.pack_host(b[5], 650), b[6], b[7]]
+        return trim_batch_host(full, base.vocab_size)
+
+    def on_device(h):
+        n, nodes = h[0].shape[0], h[0].shape[1] + h[7].shape[1] + h[4].shape[1]
+        d = [x.to(DEV) if torch.is_tensor(x) else x for x in h]
+        d[5] = PackedEdges.from_host(*h[5], n, nodes, DEV)
+        return d
+    hosts = [host(0, 8), host(8, 16), host(40, 48), host(100, 105)]          # the last one is a short batch
+    shapes = {(h[0].shape[0], h[0].shape[1], h[7].shape[1], h[4].shape[1]) for h in hosts}
+    assert len(shapes) == 4
+    dp = DataParallelStep(m_eager, lambda ps: torch.optim.SGD(ps, lr=2e-3))
+    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=2e-3))
+    for k in [0, 1, 2, 3, 0, 2, 1, 3, 3, 0, 1]:
+        loss_e, _ = dp.step(on_device(hosts[k]))
+        ls, n = eng.step(hosts[k])
+        loss_g = (ls / n).item()
+        assert abs(loss_g - loss_e.item()) <= 2e-4 * abs(loss_e.item()), (k, loss_g, loss_e.item())
+    assert len(eng.captured) == 4 and all(c.graph is not None for c in eng.captured.values())
+    assert eng.pool is not None
+    for (k, p), (_, q) in zip(m_eager.named_parameters(), m_graph.named_parameters()):
+        if p.grad is None:
+            continue
+        assert torch.allclose(p, q, rtol=0, atol=5e-4), k
