@@ -9,15 +9,38 @@ What is kept from the reference:
     through the commit's own diff / sub-token ids; the loop stops when every beam of every sample ended.
 What changes: the encoder memory is computed once, ALL live beams go through the decoder in one
 batched call, and only position `step` is pushed through the output head (the reference recomputes the
-full 30 x 25,020 distribution per beam and reads one row of it).
+full 30 x 25,020 distribution per beam and reads one row of it).  mode="incremental" / "graph" evaluates
+only the newest decoder row per step against cached keys/values (incremental.IncrementalDecoder; "graph"
+replays each step's kernels as a CUDA graph); mode="full" re-runs the 30-position decoder every step.
+The default comes from FIRA_BEAM_MODE (default "full").
 """
+import os
+import weakref
+
 import torch
+
+from .incremental import IncrementalDecoder
+
+
+_DECODERS = weakref.WeakKeyDictionary()          # model -> {(B, K, ...): IncrementalDecoder}
+
+
+def _incremental_decoder(model, B, K, tar_len, mem_len, graphs):
+    """IncrementalDecoder instances (static buffers, captured graphs) are kept per model and (B, K, mode)."""
+    store = _DECODERS.setdefault(model, {})
+    key = (B, K, tar_len, mem_len, bool(graphs), model.precision)
+    if key not in store:
+        store[key] = IncrementalDecoder(model.decoder, B, K, tar_len, mem_len, graphs=graphs)
+    return store[key]
 
 
 @torch.no_grad()
 def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, tar_len=30, start_id, eos_id,
-                pad_id=0):
+                pad_id=0, mode=None):
     """-> (sequences [B, beam, tar_len] int64 padded with pad_id, lengths [B, beam], probs [B, beam])."""
+    mode = mode or os.environ.get("FIRA_BEAM_MODE", "full")
+    if mode not in ("full", "incremental", "graph"):
+        raise ValueError("beam search mode must be 'full', 'incremental' or 'graph'")
     dev = model.out_fc.weight.device
     sou, mark, ast_change, sub_token = (t.to(dev) for t in (sou, mark, ast_change, sub_token))
     B, K = sou.shape[0], beam_size
@@ -33,6 +56,9 @@ def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, t
     prob = torch.zeros((B, K), dtype=torch.float32, device=dev)
     prob[:, 0] = 1.0
     ar = torch.arange(B, device=dev)
+    inc = None
+    if mode != "full":
+        inc = _incremental_decoder(model, B, K, tar_len, memory.shape[1], mode == "graph").start(memory, mem_mask)
 
     for step in range(tar_len - 1):
         last = seq.gather(2, (length - 1).unsqueeze(-1)).squeeze(-1)
@@ -42,10 +68,14 @@ def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, t
             break
         n_live = len(live)
         live_t = torch.tensor(live, device=dev)
-        tokens = seq[:, live_t].reshape(B * n_live, tar_len)
         mem_rep = memory.unsqueeze(1).expand(B, n_live, -1, -1).reshape(B * n_live, memory.shape[1], -1)
         mask_rep = mem_mask.unsqueeze(1).expand(B, n_live, -1).reshape(B * n_live, -1)
-        dec = model.decoder(tokens, mem_rep, mask_rep, tokens != pad_id)[:, step:step + 1]   # only row `step`
+        if inc is None:
+            tokens = seq[:, live_t].reshape(B * n_live, tar_len)
+            dec = model.decoder(tokens, mem_rep, mask_rep, tokens != pad_id)[:, step:step + 1]   # only row `step`
+        else:                                          # newest row of every beam against the K/V caches
+            row = inc.step(seq[:, :, step].reshape(B * K), step, pad_id)
+            dec = row.view(B, K, -1)[:, live_t].reshape(B * n_live, 1, -1)
         gen = torch.softmax(model.out_fc(dec), dim=-1)
         copy, gate = model.copy_net(mem_rep, dec)
         copy = torch.softmax(copy.masked_fill(~mask_rep.unsqueeze(1), -1e9), dim=-1)
@@ -74,6 +104,8 @@ def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, t
         cur = new_seq.gather(2, pos.unsqueeze(-1)).squeeze(-1)
         new_seq.scatter_(2, pos.unsqueeze(-1), torch.where(grow, tok, cur).unsqueeze(-1))
         seq, length, prob = new_seq, new_len + grow.long(), top_p
+        if inc is not None:
+            inc.reorder((ar.unsqueeze(1) * K + src_beam).reshape(-1))
     return seq, length, prob
 
 

@@ -23,7 +23,10 @@ def _need_cuda():
         pytest.skip("no CUDA device")
 
 
-def test_beam_search_ids_match_reference_test_loop():
+@pytest.mark.parametrize("mode", ["full", "incremental", "graph"])
+def test_beam_search_ids_match_reference_test_loop(mode):
+    """mode: full decoder re-run per step / KV-cached newest row / the same replayed as CUDA graphs
+    (first batch captures, later batches replay)"""
     from fira_icse_b200.beam import beam_search, best_sequences
     gold = np.load(os.path.join(GOLDEN, "beam_first16.npz"))
     raw = load_raw_golden()
@@ -37,7 +40,7 @@ def test_beam_search_ids_match_reference_test_loop():
         b = golden_batch(lo, lo + bs)
         seq, length, prob = beam_search(model, b[0], b[3], b[4], b[5].to(DEV), b[7], beam_size=int(gold["beam"]),
                                         tar_len=30, start_id=vocab["<start>"], eos_id=vocab["<eos>"],
-                                        pad_id=vocab["<pad>"])
+                                        pad_id=vocab["<pad>"], mode=mode)
         best, blen = best_sequences(seq, length, prob)
         for i in range(bs):
             ref = gold["beam_ids"][lo + i]

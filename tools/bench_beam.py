@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--trim", action="store_true", help="loader-side padding trimming (data.trim_batch_host)")
+    ap.add_argument("--modes", default="full,incremental,graph")
     a = ap.parse_args()
     import torch
     import __graft_entry__
@@ -40,11 +41,14 @@ def main():
     for B in (int(x) for x in a.batches.split(",")):
         hb = bench.host_batch(10_000, B, pin=False, trim=a.trim)
         b = bench.device_batch(hb, dev, B)
-        for K in (int(x) for x in a.beams.split(",")):
+        for K, mode in ((int(x), m) for x in a.beams.split(",") for m in a.modes.split(",")):
             def run():
                 return beam_search(model, b[0], b[3], b[4], b[5], b[7], beam_size=K, tar_len=30, start_id=1, eos_id=2,
-                                   pad_id=0)
-            run()                                                    # warm-up (lazy CUDA state, weight casts)
+                                   pad_id=0, mode=mode)
+            ref = run()                                              # warm-up (lazy CUDA state, graph capture)
+            if mode == "full":
+                ref_full = ref
+            same = bool(torch.equal(ref[0], ref_full[0])) if "full" in a.modes.split(",") else None
             torch.cuda.synchronize()
             n0 = _lib.LAUNCH_COUNT
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,9 +61,11 @@ def main():
             print(json.dumps({
                 "metric": "beam-search inference throughput", "unit": "commits/s", "value": B / ms * 1e3,
                 "ms_per_batch": ms, "batch": B, "beam": K, "decoded_steps": int(length.max().item()) - 1,
-                "precision": a.precision, "trimmed": bool(a.trim), "data": "synthetic (DataSet distribution), random weights",
+                "precision": a.precision, "mode": mode, "ids_equal_full_mode": same, "trimmed": bool(a.trim), "data": "synthetic (DataSet distribution), random weights",
                 "c_abi_calls_per_batch": (_lib.LAUNCH_COUNT - n0) // a.reps,
-                "note": "full decoder re-run per step over all live beams; encoder once per batch"}), flush=True)
+                "note": "encoder once per batch; full = 30-position decoder re-run per step over all live beams, "
+                        "incremental = newest row against K/V caches, graph = the same as CUDA-graph replays"}),
+                  flush=True)
 
 
 if __name__ == "__main__":
