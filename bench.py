@@ -419,6 +419,30 @@ def run_gpu_arm(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
+    # ---- the same, fed by the native loader: packed split arrays -> C++ gather/trim/CSR pack into pinned staging
+    #      buffers on a background thread (data.PackedBatchLoader) -> H2D -> graph replay -> loss D2H
+    loader_info = None
+    if args.graph and args.trim:
+        from fira_icse_b200.data import PackedBatchLoader
+        from fira_icse_b200.synth import SynthDataset
+        ds = SynthDataset(rank * N_POOL * B, N_POOL * B, VOCAB, AST_VOCAB)      # the commits of pool_host, in order
+        ld = PackedBatchLoader(ds, B, VOCAB, shuffle=False, multiples=(8, 8, 8), prefetch=2)
+
+        def epochs():
+            while True:
+                yield from ld
+        stream_of_batches = epochs()
+
+        def loader_step(i):
+            eng.step(next(stream_of_batches))
+            last_loss[0] = (eng.loss_sum / eng.n_local).item()
+        for i in range(N_POOL):                                       # every shape the loader emits is captured
+            loader_step(i)
+        ms_ld = timed(loader_step, args.steps)
+        loader_info = {"value": world * B * args.steps / (ms_ld * 1e-3), "unit": "commits/s",
+                       "ms_per_step": ms_ld / args.steps,
+                       "api": "PackedBatchLoader (fira_host_gather_batch, pinned staging ring) -> GraphedTrainStep.step"}
+
     # ---- the reference-facing call with the reference's own input format: dense fp64 adjacency on the host
     dense_info = None
     if rank == 0 and world == 1:
@@ -492,6 +516,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "commits/s", "h2d_bytes_per_step": int(h2d_bytes(pool_host[0])),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "api": "TransModel.forward(sou,tar,attr,mark,ast_change,PackedEdges,tar_label,sub_token,'train')"},
+            "e2e_loader": loader_info,
             "e2e_dense_edge": dense_info,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_scatter_fp32": roof_f32,
             "roofline_gemm": roof_gemm,

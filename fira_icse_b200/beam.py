@@ -12,7 +12,8 @@ batched call, and only position `step` is pushed through the output head (the re
 full 30 x 25,020 distribution per beam and reads one row of it).  mode="incremental" / "graph" evaluates
 only the newest decoder row per step against cached keys/values (incremental.IncrementalDecoder; "graph"
 replays each step's kernels as a CUDA graph); mode="full" re-runs the 30-position decoder every step.
-The default comes from FIRA_BEAM_MODE (default "full").
+The default comes from FIRA_BEAM_MODE (default "graph").  Ranking keeps the reference's candidate layout; only
+the first `beam_size` entries of its descending sort are ever used, so the sort is a device top-k.
 """
 import os
 import weakref
@@ -38,7 +39,7 @@ def _incremental_decoder(model, B, K, tar_len, mem_len, graphs):
 def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, tar_len=30, start_id, eos_id,
                 pad_id=0, mode=None):
     """-> (sequences [B, beam, tar_len] int64 padded with pad_id, lengths [B, beam], probs [B, beam])."""
-    mode = mode or os.environ.get("FIRA_BEAM_MODE", "full")
+    mode = mode or os.environ.get("FIRA_BEAM_MODE", "graph")
     if mode not in ("full", "incremental", "graph"):
         raise ValueError("beam search mode must be 'full', 'incremental' or 'graph'")
     dev = model.out_fc.weight.device
@@ -63,7 +64,7 @@ def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, t
     for step in range(tar_len - 1):
         last = seq.gather(2, (length - 1).unsqueeze(-1)).squeeze(-1)
         finished = last == eos_id                                                       # [B, K]
-        live = [j for j in range(K) if not bool(finished[:, j].all())]
+        live = [j for j, done in enumerate(finished.all(0).tolist()) if not done]      # one host sync per step
         if not live:
             break
         n_live = len(live)
@@ -88,8 +89,7 @@ def beam_search(model, sou, mark, ast_change, edge, sub_token, *, beam_size=3, t
         slot_ok = torch.arange(K, device=dev).unsqueeze(0) < n_fin
         ends_prob = torch.where(slot_ok, prob.gather(1, order), torch.full_like(prob, -1.0))
         cand = torch.cat((dist.view(B, n_live * C), ends_prob), dim=1)
-        top_p, top_i = torch.sort(cand, descending=True, dim=-1)
-        top_p, top_i = top_p[:, :K], top_i[:, :K]
+        top_p, top_i = torch.topk(cand, K, dim=-1)          # == sort(descending=True)[:K] (run_model.py:300-303)
         which_beam = top_i // C
         which_tok = top_i % C
         carried = which_beam == n_live                                                   # "keep a finished beam"

@@ -98,6 +98,30 @@ def synth_batch(first_index, batch_size, vocab_size=24650, ast_vocab_size=71):
     return ids, coo
 
 
+class SynthDataset:
+    """`n` synthetic commits in the packed split format of data.TransDataset (`.d` arrays + the length
+    attributes), so that data.PackedBatchLoader can serve them exactly like a processed DataSet split."""
+
+    diff_len, sub_token_len, ast_change_len, msg_len = N_CODE, N_SUB, N_AST, T_LEN
+
+    def __init__(self, first_index, n, vocab_size=24650, ast_vocab_size=71):
+        commits = [synth_commit(first_index + i, vocab_size, ast_vocab_size) for i in range(n)]
+        self.d = {k: np.stack([c[k] for c in commits]).astype(np.int32) for k in
+                  ("sou", "tar", "mark", "ast_change", "tar_label", "sub_token")}
+        deg, col, val, ptr = [], [], [], [0]
+        for c in commits:
+            order = np.lexsort((c["col"], c["row"]))                 # CSR order: by row, then by column
+            deg.append(np.bincount(c["row"], minlength=N_NODES).astype(np.uint8))
+            col.append(c["col"][order].astype(np.int16))
+            val.append(c["val"][order])
+            ptr.append(ptr[-1] + len(order))
+        self.d.update(deg=np.stack(deg), col=np.concatenate(col), val=np.concatenate(val),
+                      edge_ptr=np.array(ptr, np.int64))
+
+    def __len__(self):
+        return len(self.d["sou"])
+
+
 def synth_stress_graphs(first_index, batch_size, n_nodes=2048, edges_per_relation=16384, relations=4):
     """BASELINE.json config 5: per graph 4 relations x 16,384 undirected edges drawn uniformly, symmetrised,
     + self loops, degree-normalised.  -> list of (row, col, val)."""

@@ -184,3 +184,21 @@ def test_trim_batch_host_keeps_real_rows_and_renumbers():
     lf, lt = full[6], trim[6]
     sub = lf >= V + 210
     assert torch.equal(lt[~sub], lf[~sub]) and torch.equal(lt[sub], lf[sub] - (210 - c0))
+
+
+def test_synth_dataset_through_native_loader_equals_bench_host_batches():
+    """bench.py's `e2e_loader` arm: SynthDataset served by PackedBatchLoader == the batches bench.py builds in Python"""
+    import bench
+    from fira_icse_b200.data import PackedBatchLoader
+    from fira_icse_b200.synth import SynthDataset
+    ds = SynthDataset(100, 12, bench.VOCAB, bench.AST_VOCAB)
+    ld = PackedBatchLoader(ds, 6, bench.VOCAB, shuffle=False, multiples=(8, 8, 8), pin=False)
+    n = 0
+    for k, got in enumerate(ld):
+        t, csr, _ = bench.host_batch(100 + 6 * k, 6, pin=False, trim=True)
+        for j, key in ((0, "sou"), (1, "tar"), (3, "mark"), (4, "ast_change"), (6, "tar_label"), (7, "sub_token")):
+            assert torch.equal(got[j], t[key]), (k, key)
+        for a, b in zip(got[5], csr):
+            assert a.dtype == b.dtype and torch.equal(a, b), k
+        n += 1
+    assert n == 2
