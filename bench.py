@@ -426,12 +426,11 @@ def run_gpu_arm(args):
         from fira_icse_b200.data import PackedBatchLoader
         from fira_icse_b200.synth import SynthDataset
         ds = SynthDataset(rank * N_POOL * B, N_POOL * B, VOCAB, AST_VOCAB)      # the commits of pool_host, in order
-        ld = PackedBatchLoader(ds, B, VOCAB, shuffle=False, multiples=(8, 8, 8), prefetch=2)
-
-        def epochs():
-            while True:
-                yield from ld
-        stream_of_batches = epochs()
+        import numpy as np
+        laps = (args.steps + N_POOL) // N_POOL + 2                   # one long epoch cycling through the same batches
+        ld = PackedBatchLoader(ds, B, VOCAB, shuffle=False, multiples=(8, 8, 8), prefetch=2,
+                               indices=np.tile(np.arange(N_POOL * B), laps))
+        stream_of_batches = iter(ld)
 
         def loader_step(i):
             eng.step(next(stream_of_batches))
