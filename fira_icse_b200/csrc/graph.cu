@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(const int* __restrict__ r
 // fp32).  A warp then carries two independent rows, i.e. twice the rows -- and twice the dependent
 // rowptr -> (col,val) -> feature-row chains -- in flight for the same number of resident warps; the bf16
 // rows (512 B) are too short for a full warp to keep enough bytes in flight (v1: 0.29 of peak in bf16).
+// A lane's features are INTERLEAVED in 8-feature chunks (chunk j of lane l = features j*LPR*8 + l*8 .. +7), so
+// one load/store instruction of a row group covers a contiguous LPR*16 B (bf16) span; with the blocked layout
+// (lane l = features l*F ..) every instruction touched half of each 32-B sector (ncu: 49 % excessive sectors).
 template <typename T, int LPR>     // LPR lanes per destination row (16 or 8): 32/LPR rows in flight per warp
 __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                             const float* __restrict__ val, const T* __restrict__ x,
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restric
     float acc[F];
     if (addend) {
 #pragma unroll
-      for (int q = 0; q < F; q += 8) Act<T>::load8(addend + r * D + hl * F + q, acc + q);
+      for (int q = 0; q < F; q += 8) Act<T>::load8(addend + r * D + q * LPR + hl * 8, acc + q);
     } else {
 #pragma unroll
       for (int k = 0; k < F; ++k) acc[k] = 0.f;
@@ -213,15 +216,15 @@ __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restric
         const int c0 = __shfl_sync(hmask, c, hbase + t);
         const float w0 = __shfl_sync(hmask, w, hbase + t);
         float v0[F];
-        const T* p0 = x + seg_row(s, b, c0) * D + hl * F;
+        const T* p0 = x + seg_row(s, b, c0) * D + hl * 8;
 #pragma unroll
-        for (int q = 0; q < F; q += 8) Act<T>::load8(p0 + q, v0 + q);
+        for (int q = 0; q < F; q += 8) Act<T>::load8(p0 + q * LPR, v0 + q);
 #pragma unroll
         for (int k = 0; k < F; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < F; q += 8) Act<T>::store8(y + r * D + hl * F + q, acc + q);
+    for (int q = 0; q < F; q += 8) Act<T>::store8(y + r * D + q * LPR + hl * 8, acc + q);
   }
 }
 

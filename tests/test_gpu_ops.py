@@ -236,6 +236,19 @@ def test_csr_from_dense_and_aggregate_match_dense_bmm():
         if addend is not None:
             ref = ref + addend.double()
         close(y, ref, rtol=1e-5, atol=1e-5)
+        # bf16 activations (throughput mode kernel, half a warp per row): same sums on the bf16-rounded inputs,
+        # fp32 accumulation, one bf16 rounding of the result
+        x16 = x.to(torch.bfloat16)
+        a16 = addend.to(torch.bfloat16) if addend is not None else None
+        y16 = torch.empty_like(x16)
+        _lib.call("fira_gcn_aggregate", pe.rowptr.data_ptr(), pe.col.data_ptr(), pe.val.data_ptr(), x16.data_ptr(),
+                  a16.data_ptr() if a16 is not None else None, y16.data_ptr(), B, 210, 160, 280, 256, 1, st)
+        xb[perm] = x16.double()
+        ref16 = torch.bmm(edge.to(DEV).float().double(), xb.view(B, 650, 256)).view(B * 650, 256)[perm]
+        if a16 is not None:
+            ref16 = ref16 + a16.double()
+        assert torch.equal(y16, ref16.to(torch.float32).to(torch.bfloat16)) or \
+            (y16.double() - ref16).abs().max().item() <= 2 ** -7 * ref16.abs().max().item()
     rs = pe.rowsum(210, 160, 280)
     close(rs, edge.float().double().sum(-1).view(-1).to(DEV)[perm], rtol=1e-6, atol=1e-6)
     # packed-from-COO path (what the loader emits) is identical to dense->CSR

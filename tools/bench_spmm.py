@@ -59,10 +59,12 @@ def run(name, coo, N, segs, dtype_code=0):
 
 
 if __name__ == "__main__":
-    for B in (64, 256):
+    for B in ((64,) if "--b64-only" in sys.argv else (64, 256)):
         _, coo = synth_batch(0, B)
         run(f"dataset-like B={B}", coo, 650, (210, 160, 280), 0)
         run(f"dataset-like B={B}", coo, 650, (210, 160, 280), 1)
+    if "--b64-only" in sys.argv:
+        sys.exit(0)
     g = synth_stress_graphs(0, 32)
     run("stress N=2048 16k edges/relation B=32", g, 2048, (2048, 0, 0), 0)
     run("stress N=2048 16k edges/relation B=32", g, 2048, (2048, 0, 0), 1)
