@@ -256,8 +256,9 @@ def spmm_roofline(dev, hb, B, bf16=False):
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath) and not bf16:
-        traffic = json.load(open(tpath)).get("fira_gcn_aggregate_dram_bytes_per_launch")
+    if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu captures
+        traffic = json.load(open(tpath)).get("fira_gcn_aggregate_bf16_dram_bytes_per_launch" if bf16 else
+                                             "fira_gcn_aggregate_dram_bytes_per_launch")
     kname = "csr_spmm_part_kernel<bf16,16>" if bf16 else "csr_spmm_kernel<float>"
     return {"bound": "hbm", "kernel": kname + " (fira_gcn_aggregate, the GNN scatter)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
