@@ -130,7 +130,8 @@ class IncrementalDecoder:
         else:                                   # keep the addresses the graphs captured
             for old, cur in zip(self.w["layers"], new["layers"]):
                 for k in old:
-                    old[k].copy_(cur[k]) if old[k].data_ptr() != cur[k].data_ptr() else None
+                    if old[k].data_ptr() != cur[k].data_ptr():      # views of unchanged parameters need no copy
+                        old[k].copy_(cur[k])
             for k in ("Wkv", "bkv"):
                 self.w[k].copy_(new[k])
             if self.w["emb"].data_ptr() != new["emb"].data_ptr():

@@ -78,3 +78,17 @@ def test_incremental_rows_equal_full_decoder_under_beam_reordering():
     # a second batch on the same instance starts from clean caches
     inc.start(memory.flip(0), mem_mask.flip(0))
     assert int(inc.tok_mask.sum()) == 0 and float(inc.kv_self.abs().sum()) == 0.0
+    # parameters updated in place (a training step between two evaluations): the prepared weights follow
+    with torch.no_grad():
+        for p in dec.parameters():
+            p.mul_(1.05)
+    sd2 = {"decoder." + k: v.detach() for k, v in dec.state_dict().items()}
+    inc.start(memory, mem_mask)
+    tok = torch.full((B * K,), 1, dtype=torch.long)
+    with torch.no_grad():
+        got = inc.step(tok, 0, 0).clone()
+        seq0 = torch.zeros(B * K, T, dtype=torch.long)
+        seq0[:, 0] = 1
+        full = O.decoder(sd2, seq0, memory.repeat_interleave(K, 0), mem_mask.repeat_interleave(K, 0)[:, None, None, :],
+                         seq0 != 0)
+    assert torch.allclose(got, full[:, 0], atol=2e-5, rtol=1e-5)

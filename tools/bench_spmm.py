@@ -59,6 +59,12 @@ def run(name, coo, N, segs, dtype_code=0):
 
 
 if __name__ == "__main__":
+    if "--stress-sweep" in sys.argv:           # BASELINE.json config 5: per-GPU batch sweep 32 ... 256 graphs of 2048 nodes
+        for B in (32, 64, 128, 256):
+            g = synth_stress_graphs(0, B)
+            run(f"stress N=2048 16k edges/relation B={B}", g, 2048, (2048, 0, 0), 0)
+            run(f"stress N=2048 16k edges/relation B={B}", g, 2048, (2048, 0, 0), 1)
+        sys.exit(0)
     for B in ((64,) if "--b64-only" in sys.argv else (64, 256)):
         _, coo = synth_batch(0, B)
         run(f"dataset-like B={B}", coo, 650, (210, 160, 280), 0)
