@@ -228,108 +228,6 @@ __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restric
   }
 }
 
-// Version 5 (dense graphs: BASELINE.json config 5, 2048 nodes x mean degree 64): feature-sliced gather out of
-// SHARED MEMORY.  v1/v4 fetch a whole neighbour row per edge from L2 -- 64 x the algorithmic bytes on those
-// graphs (4.3 GB of L2->SM traffic per 32-graph launch, profiles/spmm_variants_r1.md).  Here one CTA owns
-// (graph b, feature slice f): it stages the slice of ALL the graph's nodes ([N][FS] + 16 B row padding against
-// bank conflicts, 160 KB for N = 2048) and the graph's rowptr once, then every warp walks destination rows and
-// gathers from shared memory: four lanes per edge (16 B = VPL features each), eight edges per warp step, the
-// eight partial sums folded by shuffles at the end of the row.  L2->SM traffic drops to the slice itself plus
-// col/val once per slice (D/FS passes).  col/val of the NEXT row are prefetched while the current row is reduced.
-template <typename T> struct Vec16;                    // 16-byte vector access: 4 fp32 or 8 bf16
-template <> struct Vec16<float> {
-  static constexpr int N = 4;
-  static __device__ __forceinline__ void load(const float* p, float* v) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float* v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-};
-template <> struct Vec16<__nv_bfloat16> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) { Act<__nv_bfloat16>::load8(p, v); }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) { Act<__nv_bfloat16>::store8(p, v); }
-};
-
-template <typename T>
-__global__ void __launch_bounds__(1024) csr_spmm_sliced_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                               const float* __restrict__ val, const T* __restrict__ x,
-                                                               const T* __restrict__ addend, T* __restrict__ y, Segs s,
-                                                               int N) {
-  constexpr int VPL = Vec16<T>::N;                 // features per lane
-  constexpr int LE = 4;                            // lanes per edge
-  constexpr int FS = VPL * LE;                     // features per slice: 16 (fp32) / 32 (bf16) = 64 B
-  constexpr int PITCH = FS + VPL;                  // row pitch in elements: 64 B + 16 B padding
-  constexpr int EPW = 32 / LE;                     // edges per warp step
-  constexpr int NSL = D / FS;
-  extern __shared__ __align__(16) unsigned char sliced_smem[];
-  T* xs = reinterpret_cast<T*>(sliced_smem);                                   // [N][PITCH]
-  int* rp = reinterpret_cast<int*>(sliced_smem + (size_t)N * PITCH * sizeof(T));   // [N + 1]
-  const int b = blockIdx.x / NSL, f0 = (blockIdx.x % NSL) * FS;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int idx = threadIdx.x; idx < N * LE; idx += blockDim.x) {
-    const int c = idx / LE, k = idx % LE;
-    *reinterpret_cast<uint4*>(xs + (size_t)c * PITCH + k * VPL) =
-        *reinterpret_cast<const uint4*>(x + seg_row(s, b, c) * D + f0 + k * VPL);
-  }
-  for (int idx = threadIdx.x; idx <= N; idx += blockDim.x) rp[idx] = rowptr[(long)b * N + idx];
-  __syncthreads();
-  const int eg = lane / LE, el = lane % LE;
-  int i = warp;
-  int e0 = 0, e1 = 0, c = 0;
-  float w = 0.f;
-  if (i < N) {
-    e0 = rp[i]; e1 = rp[i + 1];
-    if (lane < e1 - e0) { c = col[e0 + lane]; w = val[e0 + lane]; }
-  }
-  while (i < N) {
-    const int inext = i + nwarps;                  // prefetch the first 32 edges of this warp's next row
-    int ne0 = 0, ne1 = 0, cn = 0;
-    float wn = 0.f;
-    if (inext < N) {
-      ne0 = rp[inext]; ne1 = rp[inext + 1];
-      if (lane < ne1 - ne0) { cn = col[ne0 + lane]; wn = val[ne0 + lane]; }
-    }
-    float acc[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) acc[k] = 0.f;
-    for (int eb = e0; eb < e1; eb += 32) {
-      if (eb != e0) {
-        c = 0; w = 0.f;
-        if (lane < e1 - eb) { c = col[eb + lane]; w = val[eb + lane]; }
-      }
-      const int n = min(32, e1 - eb);
-#pragma unroll 4
-      for (int t = 0; t < n; t += EPW) {           // lanes past the row's end carry w = 0, c = 0 (a valid node)
-        const int c0 = __shfl_sync(0xffffffffu, c, t + eg);
-        const float w0 = __shfl_sync(0xffffffffu, w, t + eg);
-        float v[VPL];
-        Vec16<T>::load(xs + (size_t)c0 * PITCH + el * VPL, v);
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) acc[k] = fmaf(w0, v[k], acc[k]);
-      }
-    }
-#pragma unroll
-    for (int off = LE; off < 32; off <<= 1) {
-#pragma unroll
-      for (int k = 0; k < VPL; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
-    }
-    if (eg == 0) {
-      const long r = seg_row(s, b, i);
-      if (addend) {
-        float a[VPL];
-        Vec16<T>::load(addend + r * D + f0 + el * VPL, a);
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) acc[k] += a[k];
-      }
-      Vec16<T>::store(y + r * D + f0 + el * VPL, acc);
-    }
-    i = inext; e0 = ne0; e1 = ne1; c = cn; w = wn;
-  }
-}
-
 // Version 3: bulk-async (TMA engine, SASS UBLKCP) staging of the neighbour rows in shared memory.
 // Little's law on B200 asks for ~45 KB of reads in flight per SM; v1/v2 hold the gathered rows in
 // registers and spend most of a row's life on the two dependent metadata round trips, so they sit at
@@ -541,25 +439,8 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     int grid = (int)(ctas < cap ? ctas : cap);
     DISPATCH_T(dtype, csr_spmm_bulk_kernel<T, WARPS><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
-  } else if (variant == 5) {                 // dense graphs: shared-memory-resident feature slices
-    const size_t esz = dtype == FIRA_F32 ? 4 : 2;
-    const size_t smem = (size_t)N * 80 + (size_t)(N + 1) * 4;      // 64-B slice + 16-B padding per node, rowptr
-    const size_t limit = 227 * 1024;
-    FIRA_CHECK_ARG(smem <= limit, FIRA_ERR_SHAPE,
-                   "gcn_aggregate: variant 5 stages a whole graph per CTA (%zu B of shared memory > %zu)", smem, limit);
-    static bool attr5_done = false;
-    if (!attr5_done) {
-      cudaFuncSetAttribute(csr_spmm_sliced_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-      cudaFuncSetAttribute(csr_spmm_sliced_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)limit);
-      attr5_done = true;
-    }
-    const int slices = (int)(D * esz / 64);     // 16 fp32 / 8 bf16 slices of 64 B
-    const int threads = smem > 113 * 1024 ? 1024 : 512;
-    DISPATCH_T(dtype, csr_spmm_sliced_kernel<T><<<B * slices, threads, smem, (cudaStream_t)stream>>>(
-        rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else {
-    fira_set_error(FIRA_ERR_ARG, "gcn_aggregate: unknown FIRA_SPMM_VARIANT %d (1, 3, 4, 5)", variant);
+    fira_set_error(FIRA_ERR_ARG, "gcn_aggregate: unknown FIRA_SPMM_VARIANT %d (1, 3, 4)", variant);
     return FIRA_ERR_ARG;
   }
   FIRA_CHECK_LAUNCH("fira_gcn_aggregate");

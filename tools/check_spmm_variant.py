@@ -3,7 +3,7 @@
 against an fp64 index_add reference: DataSet-like 3-segment batches (with and without addend) and the
 config-5 stress graphs.  Prints one JSON line per case; exits non-zero on a mismatch.
 
-    FIRA_SPMM_VARIANT=5 python tools/check_spmm_variant.py [--time]
+    FIRA_SPMM_VARIANT=3 python tools/check_spmm_variant.py [--time]      (1, 3, 4; unset = the defaults)
 """
 import json
 import os
