@@ -28,6 +28,8 @@ PER_GPU_BATCH = 64
 VOCAB, AST_VOCAB = 24650, 71
 N_POOL = 4                      # distinct synthetic batches rotated through the timed region
 REF_BATCH = 16                  # commits per step of the CPU reference arm (bounded sample)
+WORKLOAD = ("run_model.py train, 1xB200 per-GPU batch 64 (BASELINE.json configs[1]), "
+            "synthetic commits with the DataSet node/edge distribution")
 
 
 class DotDict(dict):
@@ -207,8 +209,11 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "train_commits_per_sec", "value": value, "unit": "commits/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "run_model.py train, synthetic DataSet-like commits, reference algorithm on CPU",
-                       "per_step_batch": REF_BATCH},
+            "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH,
+                       "implementation": "reference algorithm (oracle/fira_oracle.py: dense fp64 adjacency bmm, materialised "
+                                         "copy tensor, torch Adam) on this box's host cores, fp32",
+                       "sample": f"each timed step = {REF_BATCH} commits of the same synthetic stream (a bounded sample of "
+                                 f"the {PER_GPU_BATCH}-commit batch; commits/s is per commit, batch-size independent on CPU)"},
             "cpu_baseline": {"value": value, "unit": "commits/s", "cores": threads, "kind": "port",
                              "cores_available": avail, "thread_calibration_s": calib,
                              "sample": f"{args.steps} training steps of {REF_BATCH} commits (oracle/fira_oracle.py)"},
@@ -499,9 +504,7 @@ def run_gpu_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": "run_model.py train, 1xB200 per-GPU batch 64 (BASELINE.json configs[1]), "
-                                   "synthetic commits with the DataSet node/edge distribution",
-                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "precision_mode": ("bf16 throughput (bf16 activations, tcgen05 GEMMs with fp32 TMEM accumulators, "
                                           "fp32 parameters/statistics/gradients)" if args.precision == "bf16" else
                                           "fp32 parity (fp32 storage, fp32 FFMA accumulate)"),
