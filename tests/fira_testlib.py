@@ -39,6 +39,14 @@ def load_raw_golden():
         return json.load(f)
 
 
+def load_edge_golden():
+    """(raw commits + notes, reference process_data output) of tests/golden/make_golden_edge.py: DataSet extremes and
+    crafted commits that reach the truncation branches."""
+    with gzip.open(os.path.join(GOLDEN, "raw_edge.json.gz"), "rt") as f:
+        raw = json.load(f)
+    return raw, np.load(os.path.join(GOLDEN, "batch_edge.npz"))
+
+
 def golden_batch(lo, hi, dense_edge=True, edge_dtype=torch.float64):
     """The 8-tuple Dataset.__getitem__/collate would hand the model for commits [lo, hi)."""
     g = load_batch_golden()

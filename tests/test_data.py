@@ -40,6 +40,40 @@ def test_build_commit_equals_reference_process_data():
         assert np.array_equal(attr, g["attr"][i]), (i, "attr")
 
 
+def test_builders_equal_reference_on_extreme_and_truncated_commits():
+    """tests/golden/make_golden_edge.py: the DataSet's extremes (longest diff, most AST/edit/sub-token nodes, commits
+    without AST nodes / edit nodes / sub-tokens) and crafted commits that reach the truncation branches
+    (diff > 208 tokens with edges into the cut-off part, message > 28 tokens) -- product builder (native adjacency)
+    and oracle builder against the reference's own process_data output."""
+    import graph_oracle as G
+    from fira_testlib import load_edge_golden
+    from fira_icse_b200.data import build_commit
+    edge, g = load_edge_golden()
+    base = load_raw_golden()
+    vocab, ast_vocab, upper = base["word_vocab"], base["ast_change_vocab"], base["VOCAB_UPPER_CASE"]
+    n = len(edge["notes"])
+    assert n == len(g["sou"]) >= 14 and any("crafted" in s for s in edge["notes"])
+    ptr = g["edge_ptr"]
+    for i in range(n):
+        c = build_commit(edge["raw"], i, vocab, ast_vocab, set(upper))
+        o = G.build_commit(edge["raw"], i, vocab, ast_vocab, upper)
+        ref = np.zeros((650, 650))
+        ref[g["edge_row"][ptr[i]:ptr[i + 1]], g["edge_col"][ptr[i]:ptr[i + 1]]] = g["edge_val"][ptr[i]:ptr[i + 1]]
+        mine = np.zeros((650, 650)); mine[np.repeat(np.arange(650), c["deg"]), c["col"]] = c["val"]
+        orac = np.zeros((650, 650)); orac[o["row"], o["col"]] = o["val"]
+        assert np.array_equal(ref, mine) and np.array_equal(ref, orac), edge["notes"][i]
+        for k in ("sou", "tar", "mark", "ast_change", "tar_label", "sub_token"):
+            assert np.array_equal(np.array(c[k]), g[k][i]), (edge["notes"][i], k)
+            assert np.array_equal(np.array(o[k]), g[k][i]), (edge["notes"][i], k, "oracle")
+        attr = np.zeros((210, 25), np.int64)
+        if c["attr_pos"]:
+            attr[c["attr_pos"]] = c["attr_ids"]
+        assert np.array_equal(attr, g["attr"][i]), (edge["notes"][i], "attr")
+    # the truncated diff really lost edges: no entry may touch a code node beyond the padded length
+    j = next(k for k, s in enumerate(edge["notes"]) if "230 tokens" in s)
+    assert len(edge["raw"]["difftoken"][j]) == 230 and (g["sou"][j] != 0).all()
+
+
 def test_dataset_roundtrip_and_collate(tmp_path):
     from fira_icse_b200 import PackedEdges
     from fira_icse_b200.data import TransDataset, collate_packed

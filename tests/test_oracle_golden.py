@@ -62,6 +62,30 @@ def test_oracle_forward_matches_reference(sd, gold):
     np.testing.assert_allclose(mem_abs, gold["mem_abs"][:32], rtol=1e-4)
 
 
+def test_oracle_forward_matches_reference_on_edge_commits(sd):
+    """DataSet extremes + crafted truncation commits (tests/golden/make_golden_edge.py): reference-built inputs,
+    reference model outputs (model_edge.npz)."""
+    import os
+    from fira_testlib import GOLDEN, load_edge_golden
+    _, g = load_edge_golden()
+    ref = np.load(os.path.join(GOLDEN, "model_edge.npz"))
+    n = len(g["sou"])
+    t = lambda k: torch.from_numpy(g[k].astype(np.int64))
+    ptr = g["edge_ptr"]
+    dense = torch.stack([O.dense_adjacency(g["edge_row"][ptr[i]:ptr[i + 1]], g["edge_col"][ptr[i]:ptr[i + 1]],
+                                           g["edge_val"][ptr[i]:ptr[i + 1]]) for i in range(n)])
+    batch = [t("sou"), t("tar"), t("attr"), t("mark"), t("ast_change"), dense, t("tar_label"), t("sub_token")]
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        loss_sum, n_tok = O.forward(sd, *batch, stage="train")
+        ids = O.forward(sd, *batch, stage="dev")
+        one = [O.forward(sd, *[b[i:i + 1] for b in batch], stage="train")[0].item() for i in range(n)]
+    assert int(n_tok) == int(ref["mask_sum"])
+    assert abs(loss_sum.item() - float(ref["loss_sum"])) <= 1e-4 * float(ref["loss_sum"])
+    np.testing.assert_allclose(np.array(one), ref["loss_per_commit"], rtol=1e-4)
+    assert np.array_equal(ids.numpy(), ref["argmax_ids"])
+
+
 def test_oracle_gradients_match_reference(sd, gold):
     torch.set_num_threads(8)
     n = int(gold["grad_commits"])
