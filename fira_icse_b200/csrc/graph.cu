@@ -228,6 +228,90 @@ __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restric
   }
 }
 
+// Version 6 (opt-in, FIRA_SPMM_VARIANT=6; written after the last GPU minutes of round 1, NOT YET MEASURED): the v4
+// row mapping on a persistent one-wave grid with the metadata software-pipelined two rows ahead.  ncu on v4
+// (profiles/spmm_bf16_r1_ncu_details.txt): 4.39 waves of CTAs, each living exactly one dependent chain
+// rowptr -> (col,val) -> neighbour rows (three DRAM latencies), 54 % of stall cycles on that chain.  Here a row group
+// walks ~R / (148 * 4 * 16) rows; while the neighbour rows of row k are gathered, the first (col,val) chunk of row
+// k+1 and the rowptr pair of row k+2 are already in flight, so a row costs ~one latency instead of three.
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256) csr_spmm_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                            const float* __restrict__ val, const T* __restrict__ x,
+                                                            const T* __restrict__ addend, T* __restrict__ y, Segs s,
+                                                            int N) {
+  constexpr int F = D / LPR;
+  constexpr int RPW = 32 / LPR;
+  const long R = (long)s.B * N;
+  const int lane = threadIdx.x & 31;
+  const int hl = lane % LPR;
+  const int hbase = lane - hl;
+  const unsigned hmask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << hbase;
+  const long part0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const long nparts = (long)gridDim.x * (blockDim.x >> 5) * RPW;
+  auto row_meta = [&](long r, int& b, int& lo, int& hi) {
+    int i; seg_unrow(s, r, b, i);
+    const long g = (long)b * N + i;
+    lo = rowptr[g]; hi = rowptr[g + 1];
+  };
+  long r = part0;
+  int b0 = 0, e0 = 0, e1 = 0, c = 0;             // row k: graph, edge range, first (col, val) chunk
+  float w = 0.f;
+  int b1 = 0, f0 = 0, f1 = 0;                    // row k+1: graph, edge range
+  if (r < R) {
+    row_meta(r, b0, e0, e1);
+    if (hl < e1 - e0) { c = col[e0 + hl]; w = val[e0 + hl]; }
+  }
+  if (r + nparts < R) row_meta(r + nparts, b1, f0, f1);
+  while (r < R) {
+    int cn = 0; float wn = 0.f;                  // in flight during this row: (col,val) of row k+1 ...
+    if (r + nparts < R && hl < f1 - f0) { cn = col[f0 + hl]; wn = val[f0 + hl]; }
+    int b2 = 0, g0 = 0, g1 = 0;                  // ... and the rowptr pair of row k+2
+    if (r + 2 * nparts < R) row_meta(r + 2 * nparts, b2, g0, g1);
+    float acc[F];
+    if (addend) {
+#pragma unroll
+      for (int q = 0; q < F; q += 8) Act<T>::load8(addend + r * D + q * LPR + hl * 8, acc + q);
+    } else {
+#pragma unroll
+      for (int k = 0; k < F; ++k) acc[k] = 0.f;
+    }
+    for (int eb = e0; eb < e1; eb += LPR) {
+      if (eb != e0) {                            // rows with more than LPR neighbours: later chunks are not prefetched
+        c = 0; w = 0.f;
+        if (hl < e1 - eb) { c = col[eb + hl]; w = val[eb + hl]; }
+      }
+      const int n = min(LPR, e1 - eb);
+      int t = 0;
+      for (; t + 1 < n; t += 2) {                // two neighbour rows in flight per lane
+        const int c0 = __shfl_sync(hmask, c, hbase + t), c1 = __shfl_sync(hmask, c, hbase + t + 1);
+        const float w0 = __shfl_sync(hmask, w, hbase + t), w1 = __shfl_sync(hmask, w, hbase + t + 1);
+        float v0[F], v1[F];
+        const T* p0 = x + seg_row(s, b0, c0) * D + hl * 8;
+        const T* p1 = x + seg_row(s, b0, c1) * D + hl * 8;
+#pragma unroll
+        for (int q = 0; q < F; q += 8) { Act<T>::load8(p0 + q * LPR, v0 + q); Act<T>::load8(p1 + q * LPR, v1 + q); }
+#pragma unroll
+        for (int k = 0; k < F; ++k) acc[k] = fmaf(w1, v1[k], fmaf(w0, v0[k], acc[k]));
+      }
+      if (t < n) {
+        const int c0 = __shfl_sync(hmask, c, hbase + t);
+        const float w0 = __shfl_sync(hmask, w, hbase + t);
+        float v0[F];
+        const T* p0 = x + seg_row(s, b0, c0) * D + hl * 8;
+#pragma unroll
+        for (int q = 0; q < F; q += 8) Act<T>::load8(p0 + q * LPR, v0 + q);
+#pragma unroll
+        for (int k = 0; k < F; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < F; q += 8) Act<T>::store8(y + r * D + q * LPR + hl * 8, acc + q);
+    r += nparts;
+    b0 = b1; e0 = f0; e1 = f1; c = cn; w = wn;
+    b1 = b2; f0 = g0; f1 = g1;
+  }
+}
+
 // Version 3: bulk-async (TMA engine, SASS UBLKCP) staging of the neighbour rows in shared memory.
 // Little's law on B200 asks for ~45 KB of reads in flight per SM; v1/v2 hold the gathered rows in
 // registers and spend most of a row's life on the two dependent metadata round trips, so they sit at
@@ -423,6 +507,18 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     int grid = (int)(ctas < cap ? ctas : cap);
     DISPATCH_T(dtype, csr_spmm_part_kernel<T, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+  } else if (variant == 6) {                 // persistent one-wave grid, metadata pipelined two rows ahead (unmeasured)
+    const int rows_per_cta = dtype == FIRA_BF16 ? 16 : 8;
+    long ctas = (R + rows_per_cta - 1) / rows_per_cta;
+    const long cap = 148L * 4;               // 64 registers/thread -> 4 CTAs of 256 threads per SM
+    int grid = (int)(ctas < cap ? ctas : cap);
+    if (dtype == FIRA_BF16) {
+      csr_spmm_pipe_kernel<__nv_bfloat16, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          rowptr, col, val, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)y, s, N);
+    } else {
+      csr_spmm_pipe_kernel<float, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          rowptr, col, val, (const float*)x, (const float*)addend, (float*)y, s, N);
+    }
   } else if (variant == 3) {
     constexpr int WARPS = 6;
     const size_t smem = (size_t)WARPS * EB * D * (dtype == FIRA_F32 ? 4 : 2);
@@ -440,7 +536,7 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     DISPATCH_T(dtype, csr_spmm_bulk_kernel<T, WARPS><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else {
-    fira_set_error(FIRA_ERR_ARG, "gcn_aggregate: unknown FIRA_SPMM_VARIANT %d (1, 3, 4)", variant);
+    fira_set_error(FIRA_ERR_ARG, "gcn_aggregate: unknown FIRA_SPMM_VARIANT %d (1, 3, 4, 6)", variant);
     return FIRA_ERR_ARG;
   }
   FIRA_CHECK_LAUNCH("fira_gcn_aggregate");
