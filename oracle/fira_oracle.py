@@ -13,7 +13,8 @@ gradients are the gradient reference for the CUDA backward kernels.
 
 Pinned against the unmodified reference by tests/test_oracle_golden.py using
 tests/golden/model_first128.npz (made by tests/golden/make_golden.py from
-/root/reference at commit 77b9a6a).
+/root/reference at commit 77b9a6a) and tests/golden/model_edge.npz (DataSet extremes and
+crafted truncation commits, tests/golden/make_golden_edge.py).
 
 Reference sites restated here (relative to /root/reference):
   position table .......... gnn_transformer.py:10-19

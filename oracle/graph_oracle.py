@@ -4,7 +4,8 @@ Pure-Python restatement of the per-commit part of the reference's
 ``TransDataset.process_data`` (/root/reference/Dataset.py:96-294) and ``process_edge``
 (Dataset.py:346-357).  It is the checker for fira_icse_b200.graph (the product packer),
 and is itself pinned to the reference's own output by tests/test_oracle_golden.py via
-tests/golden/batch_first128.npz.
+tests/golden/batch_first128.npz and by tests/test_data.py via tests/golden/batch_edge.npz
+(DataSet extremes and crafted commits that reach the truncation branches).
 
 Node numbering (Dataset.py:220-266): code token j -> j+1 (0 is <start>), sub-token k ->
 210+k, AST node a -> 370+a, edit node c -> 370+len(ast)+c.  Every relation is inserted
