@@ -26,6 +26,37 @@ def test_library_exports_every_symbol_the_header_declares():
     assert exported == set(protos), exported ^ set(protos)     # nothing exported that the header hides
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/fira_b200.h must compile as C99 and a C program must link against the
+    library and call it (version / error string / a host entry point; no GPU work)"""
+    import shutil
+    import subprocess
+    from fira_icse_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "fira_b200.h"
+int main(void) {
+  int pairs[2] = {0, 0};                 /* AST node 0 - code token 0 */
+  int deg[8], col[32], nnz = -1;
+  double val[32];
+  int rc = fira_host_build_adjacency(0, 0, 0, 0, pairs, 1, 0, 0, 0, 0, 1, 1, 4, 2, 2, deg, col, val, 32, &nnz);
+  if (rc != 0) { printf("error %d: %s\n", rc, fira_last_error_string()); return 1; }
+  rc = fira_host_build_adjacency(0, 0, 0, 0, pairs, 1, 0, 0, 0, 0, 1, 1, 4, 2, 2, deg, col, val, 2, &nnz);
+  printf("%d %d %d %d %s\n", fira_version(), fira_built_arch(), nnz, rc, rc ? "capacity-error-reported" : "");
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-l:libfira_b200.so", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert out[:3] == ["1", "100", "14"] and int(out[3]) != 0 and out[4] == "capacity-error-reported", out
+
+
 def test_sass_is_sm100():
     from fira_icse_b200 import _lib
     out = os.popen(f"/usr/local/cuda/bin/cuobjdump -lelf {_lib.LIB_PATH} 2>/dev/null").read()
