@@ -484,7 +484,7 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of 16 commits)
     cpu_info = None
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:          # reported at N = 1 only (rank 0 is the only rank left here)
         avail = cpu_threads()
         threads, calib = best_cpu_threads(avail)
         step = oracle_step_fn(REF_BATCH, threads)
