@@ -9,6 +9,7 @@ model's -- with raw random weights every step has p ~ 1e-4, the fp32 probability
 run_model.py:271 underflow to 0 after ~12 steps and the ranking degenerates into sort tie-breaking;
 inputs: the first N_COMMITS commits of tests/golden/batch_first128.npz, test batch 8, beam 3.
 Writes tests/golden/beam_first16.npz (chosen sequence per commit, -1 padded).
+`--beam 5` writes tests/golden/beam5_first16.npz (BASELINE.json config 4 also names beam 5).
 """
 import os
 import shutil
@@ -22,6 +23,7 @@ import torch
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 N_COMMITS, BATCH, SHARPEN = 16, 8, 20.0
+BEAM = int(sys.argv[sys.argv.index("--beam") + 1]) if "--beam" in sys.argv else 3
 
 
 def main():
@@ -44,6 +46,7 @@ def main():
     nltk.translate = tr; tr.bleu_score = stub
     sys.modules.update({"nltk": nltk, "nltk.translate": tr, "nltk.translate.bleu_score": stub})
     import run_model as R
+    R.args['beam_size'] = BEAM
 
     g = np.load(os.path.join(HERE, "batch_first128.npz"))
     ptr = g["edge_ptr"]
@@ -79,7 +82,8 @@ def main():
     out = np.full((N_COMMITS, 30), -1, np.int64)
     for i, h in enumerate(hyps):
         out[i, :len(h)] = h
-    np.savez_compressed(os.path.join(HERE, "beam_first16.npz"), beam_ids=out, batch=BATCH, beam=3, sharpen=SHARPEN)
+    name = "beam_first16.npz" if BEAM == 3 else f"beam{BEAM}_first16.npz"
+    np.savez_compressed(os.path.join(HERE, name), beam_ids=out, batch=BATCH, beam=BEAM, sharpen=SHARPEN)
     print(out[:4])
 
 
