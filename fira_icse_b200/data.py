@@ -312,12 +312,18 @@ class PackedBatchLoader:
     multiples: rounding of the trimmed (code, sub-token, AST) segment lengths; None = no trimming.
     max_shapes: upper bound on the number of distinct batch shapes ever emitted (each shape is one captured
     CUDA graph downstream); once reached, a batch is padded up to the smallest already-emitted shape that
-    holds it (the full 210/160/280 if none does)."""
+    holds it (the full 210/160/280 if none does).
+    bucket: 0 (default) keeps the reference's batching -- consecutive slices of one uniform shuffle.  bucket = K > 1
+    is an OPT-IN departure from it: the shuffled order is cut into windows of K batches, each window is sorted by
+    commit size (real code + sub-token + AST nodes) before it is sliced, and the window's batches are emitted in
+    random order.  Batches then hold commits of similar size, so trimming removes far more padding; every commit
+    is still visited exactly once per epoch, but batch composition is no longer independent of commit size."""
 
     def __init__(self, dataset, batch_size, vocab_size, shuffle=False, indices=None, multiples=(8, 8, 8),
-                 max_shapes=None, drop_last=False, prefetch=2, pin=None):
+                 max_shapes=None, drop_last=False, prefetch=2, pin=None, bucket=0):
         self.ds, self.B, self.V = dataset, int(batch_size), int(vocab_size)
         self.shuffle, self.drop_last = shuffle, drop_last
+        self.bucket = int(bucket)
         self.indices = np.arange(len(dataset), dtype=np.int64) if indices is None else np.asarray(indices, np.int64)
         self.multiples = (0, 0, 0) if multiples is None else tuple(int(m) for m in multiples)
         self.max_shapes = max_shapes
@@ -330,6 +336,7 @@ class PackedBatchLoader:
         self.col = np.ascontiguousarray(d["col"], dtype=np.int16)
         self.val = np.ascontiguousarray(d["val"], dtype=np.float64)
         self.edge_ptr = np.ascontiguousarray(d["edge_ptr"], dtype=np.int64)
+        self.size = sum((self.tab[k] != 0).sum(1) for k in ("sou", "sub_token", "ast_change"))   # real nodes per commit
         per_commit = int(np.diff(self.edge_ptr).max()) if len(self.edge_ptr) > 1 else 0
         self.edge_cap = max(1, per_commit * self.B)
         self.pin = torch.cuda.is_available() if pin is None else pin
@@ -380,15 +387,35 @@ class PackedBatchLoader:
         return slot.batch
 
     # ------------------------------------------------------------------ iteration
-    def __iter__(self):
-        import queue
-        import threading
+    def epoch_batches(self):
+        """Index arrays of one epoch's batches (draws from torch's global generator when shuffling)."""
         order = self.indices
         if self.shuffle:
             order = order[torch.randperm(len(order)).numpy()]        # torch's global generator, like DataLoader
+        if self.bucket > 1:
+            span = self.bucket * self.B
+            chunks = []
+            for lo in range(0, len(order), span):
+                win = order[lo:lo + span]
+                win = win[np.argsort(self.size[win], kind="stable")]
+                part = [win[i:i + self.B] for i in range(0, len(win), self.B)]
+                if self.shuffle and len(part) > 1:
+                    part = [part[j] for j in torch.randperm(len(part)).tolist()]
+                chunks += part
+            if self.drop_last:
+                chunks = [c for c in chunks if len(c) == self.B]
+            else:                                                   # at most one short batch per window: keep them last
+                chunks = [c for c in chunks if len(c) == self.B] + [c for c in chunks if len(c) < self.B]
+            return chunks
         chunks = [order[i:i + self.B] for i in range(0, len(order), self.B)]
         if self.drop_last and chunks and len(chunks[-1]) < self.B:
             chunks.pop()
+        return chunks
+
+    def __iter__(self):
+        import queue
+        import threading
+        chunks = self.epoch_batches()
         free_q, full_q = queue.Queue(), queue.Queue()
         for s in self.slots:
             s.event = None

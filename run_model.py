@@ -14,7 +14,8 @@ beam search ranking.  Differences, all below the module surface:
     (engine.GraphedTrainStep); FIRA_ENGINE=eager issues the same kernels launch by launch;
   * optional env overrides, defaults unchanged: FIRA_BATCH, FIRA_TEST_BATCH, FIRA_EPOCHS, FIRA_BEAM,
     FIRA_MAX_BATCHES (smoke runs), FIRA_WORKERS, FIRA_PRECISION (fp32 parity mode | bf16 throughput mode),
-    FIRA_MAX_SHAPES (bound on distinct trimmed batch shapes = captured graphs, default 24).
+    FIRA_MAX_SHAPES (bound on distinct trimmed batch shapes = captured graphs, default 24), FIRA_BUCKET (0 = the
+    reference's uniform batching; K > 1 = size-bucketed batches within windows of K batches, see PackedBatchLoader).
 """
 import json
 import os
@@ -185,7 +186,8 @@ def main_train():
     if os.environ.get("FIRA_ENGINE", "graph") == "graph":
         train_loader = PackedBatchLoader(train_set, args.batch_size, args.vocab_size, shuffle=True,
                                          indices=range(lo, hi) if WORLD > 1 else None, multiples=(8, 16, 16),
-                                         max_shapes=int(os.environ.get("FIRA_MAX_SHAPES", 24)), drop_last=WORLD > 1)
+                                         max_shapes=int(os.environ.get("FIRA_MAX_SHAPES", 24)), drop_last=WORLD > 1,
+                                         bucket=int(os.environ.get("FIRA_BUCKET", 0)))
         dp = GraphedTrainStep(model, args.batch_size, lambda ps: Adam(ps, args.lr, fused=True, capturable=True),
                               edge_capacity=train_loader.edge_cap)
     else:

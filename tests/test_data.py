@@ -182,11 +182,43 @@ def test_native_loader_equals_python_collate_and_trim(tmp_path):
     # shuffled epochs are permutations driven by torch's generator
     torch.manual_seed(3)
     sh = PackedBatchLoader(ds, 8, V, shuffle=True, pin=False)
-    first = torch.cat([b[1] for b in sh])
+    first = torch.cat([b[1].clone() for b in sh])          # batches are views of recycled staging slots
     torch.manual_seed(3)
-    again = torch.cat([b[1] for b in sh])
+    again = torch.cat([b[1].clone() for b in sh])
     assert torch.equal(first, again) and first.shape[0] == n
-    assert not torch.equal(first, torch.cat([b[1] for b in ld]))
+    assert not torch.equal(first, torch.cat([b[1].clone() for b in ld]))
+
+
+def test_bucketed_batching_visits_every_commit_once_and_trims_more(tmp_path):
+    """opt-in size-bucketed batches (PackedBatchLoader(bucket=K)): a permutation of the epoch, far fewer padded rows"""
+    from fira_icse_b200.data import PackedBatchLoader, TransDataset
+    raw = load_raw_golden()
+    _write_dataset(str(tmp_path), raw)
+    ds = TransDataset(reference_args(), "train", root=str(tmp_path))
+    V, n = len(raw["word_vocab"]), len(ds)
+
+    def epoch(loader):
+        seen, rows = [], 0
+        for b in loader:
+            seen.append(b[1].clone())                             # views of recycled staging slots
+            rows += b[0].shape[0] * (b[0].shape[1] + b[7].shape[1] + b[4].shape[1])
+        return torch.cat(seen), rows
+    torch.manual_seed(11)
+    plain_tar, plain_rows = epoch(PackedBatchLoader(ds, 8, V, shuffle=True, pin=False))
+    torch.manual_seed(11)
+    ld = PackedBatchLoader(ds, 8, V, shuffle=True, pin=False, bucket=4)
+    buck_tar, buck_rows = epoch(ld)
+    assert buck_tar.shape[0] == plain_tar.shape[0] == n
+    key = lambda t: sorted(map(tuple, t.tolist()))
+    assert key(buck_tar) == key(plain_tar)                       # same multiset of commits, each exactly once
+    assert buck_rows < 0.85 * plain_rows, (buck_rows, plain_rows)
+    sizes = [len(c) for c in ld.epoch_batches()]
+    assert sum(sizes) == n and sizes.count(8) == n // 8 and all(s == 8 for s in sizes[:n // 8])
+    assert all(len(c) == 8 for c in PackedBatchLoader(ds, 8, V, shuffle=True, pin=False, bucket=4,
+                                                      drop_last=True).epoch_batches())
+    torch.manual_seed(11)
+    again, _ = epoch(ld)
+    assert torch.equal(again, buck_tar)                           # reproducible under torch.manual_seed
 
 
 def test_trim_batch_host_keeps_real_rows_and_renumbers():
