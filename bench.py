@@ -27,7 +27,6 @@ sys.path.insert(0, ROOT)
 PER_GPU_BATCH = 64
 VOCAB, AST_VOCAB = 24650, 71
 N_POOL = 4                      # distinct synthetic batches rotated through the timed region
-REF_BATCH = 16                  # commits per step of the CPU reference arm (bounded sample)
 WORKLOAD = ("run_model.py train, 1xB200 per-GPU batch 64 (BASELINE.json configs[1]), "
             "synthetic commits with the DataSet node/edge distribution")
 
@@ -126,29 +125,6 @@ def h2d_bytes(hb):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def oracle_step_fn(batch_size, threads):
-    """Reference-algorithm training step on the host (oracle port: dense 650x650 fp64 adjacency bmm,
-    materialised copy tensor, Adam) -- run_model.py:101-109."""
-    import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import fira_oracle as O
-    torch.set_num_threads(threads)
-    params = {k: v.requires_grad_(True) for k, v in O.random_state_dict(VOCAB, AST_VOCAB).items()}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
-    pool = []
-    for i in range(2):
-        t, _, coo = host_batch(10_000 + i * batch_size, batch_size, pin=False)
-        edge = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo])     # fp64 [B,650,650] like Dataset.py:340
-        pool.append([t["sou"], t["tar"], t["attr"], t["mark"], t["ast_change"], edge, t["tar_label"], t["sub_token"]])
-    state = {"i": 0}
-
-    def step():
-        b = pool[state["i"] % len(pool)]
-        state["i"] += 1
-        return O.train_step(params, opt, b)
-    return step
-
-
 def cpu_threads():
     """Host threads this process may really use: affinity mask, capped by a cgroup CPU quota if any."""
     try:
@@ -164,32 +140,34 @@ def cpu_threads():
     return n
 
 
+def ref_worker(*argv, timeout=1500):
+    """oracle/ref_cpu_bench.py in a subprocess with CUDA_VISIBLE_DEVICES="" (the reference branches on
+    torch.cuda.is_available() globally): the UNMODIFIED reference TransModel + Adam
+    (oracle/_ref, staged by oracle/make_ref.sh) on this box's host cores.  -> parsed JSON line."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_cpu_bench.py"), *map(str, argv)],
+                       env=env, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference CPU worker failed: " + r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def best_cpu_threads(limit):
-    """torch CPU ops on a 100+ core host run SLOWER with every core (thread wake-up cost on 256-wide
-    tensors): time one small forward at a few thread counts and keep the fastest, so the CPU arm is
-    the best the box's cores can do, not a strawman."""
-    import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import fira_oracle as O
-    sd = O.random_state_dict(VOCAB, AST_VOCAB)
-    t, _, coo = host_batch(20_000, 8, pin=False)
-    edge = torch.stack([O.dense_adjacency(r, c, v) for r, c, v in coo])
-    b = [t["sou"], t["tar"], t["attr"], t["mark"], t["ast_change"], edge, t["tar_label"], t["sub_token"]]
+    """torch CPU ops on a 100+ core host run SLOWER with every core (thread wake-up cost on 256-wide tensors):
+    time one reference forward at a few thread counts and keep the fastest, so the CPU arm is the best the box's
+    cores can do, not a strawman."""
     cands = sorted({c for c in (4, 8, 16, 32, 64, limit) if c <= limit})
-    best, best_t, log = cands[0], float("inf"), {}
-    for c in cands:
-        torch.set_num_threads(c)
-        with torch.no_grad():
-            O.forward(sd, *b, stage="train")                 # warm
-            t0 = time.perf_counter()
-            O.forward(sd, *b, stage="train")
-            dt = time.perf_counter() - t0
-        log[c] = round(dt, 3)
-        if dt < best_t:
-            best, best_t = c, dt
-        if dt > 4 * best_t:
-            break
-    return best, log
+    out = ref_worker("--calibrate", ",".join(map(str, cands)))
+    return int(out["best_threads"]), out["calibration_s"]
+
+
+REF_IMPL_TEXT = {
+    "reference": "UNMODIFIED reference TransModel (oracle/_ref/{Model,gnn_transformer,combination_layer}.py, staged by "
+                 "oracle/make_ref.sh) + torch.optim.Adam, fp32, dense float64 [64,650,650] adjacency, dropout on, "
+                 "run_model.py:101-109 loop body, CUDA_VISIBLE_DEVICES='' subprocess",
+    "port": "oracle port (oracle/fira_oracle.py; oracle/_ref was not staged on this box)"}
 
 
 def run_reference_arm(args):
@@ -198,27 +176,22 @@ def run_reference_arm(args):
         return
     avail = cpu_threads()
     threads, calib = best_cpu_threads(avail)
-    step = oracle_step_fn(REF_BATCH, threads)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    value = REF_BATCH * args.steps / dt
+    out = ref_worker("--batch", PER_GPU_BATCH, "--steps", args.steps, "--warmup", args.warmup, "--threads", threads,
+                     timeout=3000)
+    dt = out["total_s"]
+    value = PER_GPU_BATCH * args.steps / dt
     line = {"impl": "reference", "metric": "train_commits_per_sec", "value": value, "unit": "commits/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH,
-                       "implementation": "reference algorithm (oracle/fira_oracle.py: dense fp64 adjacency bmm, materialised "
-                                         "copy tensor, torch Adam) on this box's host cores, fp32",
-                       "sample": f"each timed step = {REF_BATCH} commits of the same synthetic stream (a bounded sample of "
-                                 f"the {PER_GPU_BATCH}-commit batch; commits/s is per commit, batch-size independent on CPU)"},
-            "cpu_baseline": {"value": value, "unit": "commits/s", "cores": threads, "kind": "port",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH,
+                       "parallelism": "cpu",
+                       "implementation": REF_IMPL_TEXT[out["impl"]],
+                       "sample": f"each timed step = one full {PER_GPU_BATCH}-commit batch of the same synthetic stream"},
+            "cpu_baseline": {"value": value, "unit": "commits/s", "cores": threads, "kind": out["impl"],
                              "cores_available": avail, "thread_calibration_s": calib,
-                             "sample": f"{args.steps} training steps of {REF_BATCH} commits (oracle/fira_oracle.py)"},
+                             "sample": f"{args.steps} training steps of {PER_GPU_BATCH} commits after {args.warmup} warm-up"},
             "e2e": {"value": value, "unit": "commits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "last_loss": out.get("last_loss")}
     print(json.dumps(line), flush=True)
 
 
@@ -482,23 +455,16 @@ def run_gpu_arm(args):
     roof_f32 = spmm_roofline(dev, full_host, B, bf16=False) if args.precision == "bf16" else None
     roof_gemm = gemm_roofline(dev, B) if args.precision == "bf16" else None
 
-    # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of 16 commits)
+    # ---- CPU baseline on this box's host cores: the unmodified reference, same batch (bounded sample)
     cpu_info = None
     if not args.skip_cpu_baseline and world == 1:          # reported at N = 1 only (rank 0 is the only rank left here)
         avail = cpu_threads()
         threads, calib = best_cpu_threads(avail)
-        step = oracle_step_fn(REF_BATCH, threads)
-        step()
-        t0 = time.perf_counter()
-        n_cpu = 0
-        while n_cpu < 4 and (n_cpu < 1 or time.perf_counter() - t0 < 12.0):
-            step()
-            n_cpu += 1
-        cpu_dt = time.perf_counter() - t0
-        cpu_info = {"value": REF_BATCH * n_cpu / cpu_dt, "unit": "commits/s", "cores": threads, "kind": "port",
-                    "cores_available": avail, "thread_calibration_s": calib,
-                    "sample": f"{n_cpu} training steps of {REF_BATCH} commits after 1 warm-up "
-                              "(oracle/fira_oracle.py: dense fp64 adjacency bmm, materialised copy tensor, Adam)"}
+        out = ref_worker("--batch", B, "--steps", 3, "--warmup", 1, "--threads", threads)
+        cpu_info = {"value": B * len(out["step_s"]) / out["total_s"], "unit": "commits/s", "cores": threads,
+                    "kind": out["impl"], "cores_available": avail, "thread_calibration_s": calib,
+                    "sample": f"{len(out['step_s'])} training steps of {B} commits after 1 warm-up: "
+                              + REF_IMPL_TEXT[out["impl"]]}
 
     line = {"metric": "train_commits_per_sec", "value": value, "unit": "commits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

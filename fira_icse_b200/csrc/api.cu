@@ -16,7 +16,7 @@ void fira_set_error(int code, const char* fmt, ...) {
 }
 
 extern "C" {
-int fira_version(void) { return 1; }
+int fira_version(void) { return 2; }
 const char* fira_last_error_string(void) { return g_err; }
 int fira_built_arch(void) { return 100; }
 }

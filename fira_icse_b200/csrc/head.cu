@@ -212,7 +212,13 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ log
     float p = 1.f;
     if (lab != 0) {
       if (lab < V) p = g0 * (expf(Act<T>::ld(lrow + lab) - vmax) / vsum);
-      else { const int s = lab - V; p = g1 * (expf((mrow[s] ? srow[s] : kMaskFill) - cmax) / csum); }
+      else {
+        // a copy label beyond the (possibly loader-trimmed) source is never read out of bounds: it gets p = 0 -> the
+        // clamp floor, no gradient -- what the reference computes for a label on a padded (masked) source position
+        // (Model.py:61,69); beyond V+370 the reference's nll_loss raises instead (Model.py:81)
+        const int s = lab - V;
+        p = s < S ? g1 * (expf((mrow[s] ? srow[s] : kMaskFill) - cmax) / csum) : 0.f;
+      }
     }
     float* st = stats + row * 8;
     st[0] = vmax; st[1] = vsum; st[2] = cmax; st[3] = csum; st[4] = g0; st[5] = g1; st[6] = p; st[7] = 0.f;

@@ -142,6 +142,8 @@ int fira_host_gather_batch(const int* sou, const int* tar, const int* mark, cons
       o_tar[(long)b * msg_len + j] = tar[i * msg_len + j];
       long l = tar_label[i * msg_len + j];
       if (l >= vocab_size + n0) l -= (n0 - c0);          // sub-token copy labels sit behind the code segment
+      // a label that lands beyond c0 + c1 pointed at a PADDED source position of the untrimmed batch (masked there:
+      // p = 0 -> clamp floor, Model.py:61,69); head_fwd_kernel gives such labels the same p = 0 without reading them
       o_tar_label[(long)b * msg_len + j] = l;
     }
   }

@@ -294,6 +294,66 @@ __global__ void comb_gate_bwd_kernel(const T* __restrict__ qk, long ld_qk, const
   }
 }
 
+// General-value form of the same gate for the stand-alone Combination / CombinationLayer modules
+// (combination_layer.py:7-17 with an arbitrary `value` tensor instead of the 4-row mark table): q, k, v, out [rows, D].
+template <typename T>
+__global__ void comb_gate3_fwd_kernel(const T* __restrict__ qp, const T* __restrict__ kp, const T* __restrict__ vp,
+                                      T* __restrict__ out, long rows, float scale, float p_drop, uint64_t seed,
+                                      const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  if (seed_ctr) seed += *seed_ctr;
+  const int lane = threadIdx.x & 31;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * ROWS_PER_CTA) {
+    float q[8], k[8], v[8], c[8];
+    Act<T>::load8(qp + r * D + lane * 8, q);
+    Act<T>::load8(kp + r * D + lane * 8, k);
+    Act<T>::load8(vp + r * D + lane * 8, v);
+    uint32_t m = 0xffu;
+    if (p_drop > 0.f) m = dropout_keep8(seed, stream_id, (uint64_t)r * 32 + lane, p_drop);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float e = k[i] - v[i];
+      float gte = 1.f / (1.f + expf(-scale * q[i] * e));
+      float x = fmaf(gte, e, v[i]);
+      c[i] = ((m >> i) & 1) ? x * keep_scale : 0.f;
+    }
+    Act<T>::store8(out + r * D + lane * 8, c);
+  }
+}
+
+template <typename T>
+__global__ void comb_gate3_bwd_kernel(const T* __restrict__ qp, const T* __restrict__ kp, const T* __restrict__ vp,
+                                      const T* __restrict__ d_out, T* __restrict__ dqp, T* __restrict__ dkp,
+                                      T* __restrict__ dvp, long rows, float scale, float p_drop, uint64_t seed,
+                                      const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  if (seed_ctr) seed += *seed_ctr;
+  const int lane = threadIdx.x & 31;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * ROWS_PER_CTA) {
+    float q[8], k[8], v[8], go[8], dq[8], dk[8], dv[8];
+    Act<T>::load8(qp + r * D + lane * 8, q);
+    Act<T>::load8(kp + r * D + lane * 8, k);
+    Act<T>::load8(vp + r * D + lane * 8, v);
+    Act<T>::load8(d_out + r * D + lane * 8, go);
+    uint32_t m = 0xffu;
+    if (p_drop > 0.f) m = dropout_keep8(seed, stream_id, (uint64_t)r * 32 + lane, p_drop);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float dc = ((m >> i) & 1) ? go[i] * keep_scale : 0.f;
+      float e = k[i] - v[i];
+      float gte = 1.f / (1.f + expf(-scale * q[i] * e));
+      float da = dc * e * gte * (1.f - gte);
+      dq[i] = da * scale * e;
+      float de = dc * gte + da * scale * q[i];
+      dk[i] = de;
+      dv[i] = dc - de;
+    }
+    Act<T>::store8(dqp + r * D + lane * 8, dq);
+    Act<T>::store8(dkp + r * D + lane * 8, dk);
+    Act<T>::store8(dvp + r * D + lane * 8, dv);
+  }
+}
+
 // ------------------------------------------------------------------ column sums (bias gradients)
 // out[n] += sum_m x[m, n]; one warp covers 32 columns x a strided set of rows.
 template <typename T>
@@ -495,6 +555,32 @@ int fira_comb_gate_bwd(const void* qk, long ld_qk, const float* vtab, const int*
   DISPATCH_T(dtype, comb_gate_bwd_kernel<T><<<grid, CTA, 0, (cudaStream_t)stream>>>(
       (const T*)qk, ld_qk, vtab, mark, (const T*)d_out, (T*)d_qk, d_vtab, rows, scale, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate_bwd");
+  return FIRA_OK;
+}
+
+int fira_comb_gate3_fwd(const void* q, const void* k, const void* v, void* out, long rows, int dim, int d_head,
+                        float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream) {
+  FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "comb_gate3_fwd: dim %d != 256", dim);
+  FIRA_CHECK_ARG(d_head > 0, FIRA_ERR_SHAPE, "comb_gate3_fwd: d_head %d", d_head);
+  if (rows == 0) return FIRA_OK;
+  const float scale = 1.f / sqrtf((float)d_head);
+  DISPATCH_T(dtype, comb_gate3_fwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
+      (const T*)q, (const T*)k, (const T*)v, (T*)out, rows, scale, p_drop, seed, seed_ctr, stream_id);)
+  FIRA_CHECK_LAUNCH("fira_comb_gate3_fwd");
+  return FIRA_OK;
+}
+
+int fira_comb_gate3_bwd(const void* q, const void* k, const void* v, const void* d_out, void* d_q, void* d_k, void* d_v,
+                        long rows, int dim, int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr,
+                        uint32_t stream_id, int dtype, void* stream) {
+  FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "comb_gate3_bwd: dim %d != 256", dim);
+  FIRA_CHECK_ARG(d_head > 0, FIRA_ERR_SHAPE, "comb_gate3_bwd: d_head %d", d_head);
+  if (rows == 0) return FIRA_OK;
+  const float scale = 1.f / sqrtf((float)d_head);
+  DISPATCH_T(dtype, comb_gate3_bwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
+      (const T*)q, (const T*)k, (const T*)v, (const T*)d_out, (T*)d_q, (T*)d_k, (T*)d_v, rows, scale, p_drop, seed,
+      seed_ctr, stream_id);)
+  FIRA_CHECK_LAUNCH("fira_comb_gate3_bwd");
   return FIRA_OK;
 }
 

@@ -140,7 +140,9 @@ class TransDataset(Dataset):
         self.graph_len = self.diff_len + self.sub_token_len + self.ast_change_len
         self.dense_edges = dense_edges
         self.root = root
-        cache = os.path.join(root, f"processed_b200_{data_name}.npz")
+        # a truncated build (limit=N) gets its own cache name: a later full run must not pick it up
+        self._tag = f"_limit{int(limit)}" if limit else ""
+        cache = os.path.join(root, f"processed_b200_{data_name}{self._tag}.npz")
         if not os.path.exists(cache):
             self._process_all(limit)
         z = np.load(cache)
@@ -177,7 +179,7 @@ class TransDataset(Dataset):
                     cols[k].append(c[k])
                 deg.append(c["deg"]); col.append(c["col"]); val.append(c["val"]); eptr.append(eptr[-1] + len(c["col"]))
                 apos += c["attr_pos"]; aids += c["attr_ids"]; aptr.append(aptr[-1] + len(c["attr_pos"]))
-            np.savez(os.path.join(self.root, f"processed_b200_{split}.npz"),
+            np.savez(os.path.join(self.root, f"processed_b200_{split}{self._tag}.npz"),
                      **{k: np.array(v, np.int32).reshape(len(order), -1) for k, v in cols.items()},
                      deg=np.array(deg, np.uint8).reshape(len(order), self.graph_len),
                      col=np.concatenate(col) if col else np.zeros(0, np.int16),
@@ -325,6 +327,10 @@ class PackedBatchLoader:
         self.shuffle, self.drop_last = shuffle, drop_last
         self.bucket = int(bucket)
         self.indices = np.arange(len(dataset), dtype=np.int64) if indices is None else np.asarray(indices, np.int64)
+        if len(self.indices) and (self.indices.min() < 0 or self.indices.max() >= len(dataset)):
+            raise IndexError(f"PackedBatchLoader: indices must lie in [0, {len(dataset)}) "
+                             f"(got {int(self.indices.min())}..{int(self.indices.max())}); the native gather does not "
+                             "bounds-check")
         self.multiples = (0, 0, 0) if multiples is None else tuple(int(m) for m in multiples)
         self.max_shapes = max_shapes
         self.shapes = {}
@@ -417,8 +423,9 @@ class PackedBatchLoader:
         import threading
         chunks = self.epoch_batches()
         free_q, full_q = queue.Queue(), queue.Queue()
+        # slot events survive from one epoch to the next: the copies of the previous epoch's last batches may still be
+        # queued behind graph replays when the next epoch's producer starts refilling the staging slots
         for s in self.slots:
-            s.event = None
             free_q.put(s)
         stop = threading.Event()
 
@@ -454,3 +461,9 @@ class PackedBatchLoader:
             stop.set()
             free_q.put(self.slots[0])
             th.join(timeout=5)
+            if self.pin:
+                # normal end or early break: the slot handed out last has no event yet -- make sure every copy out of
+                # the staging ring has run before anybody (the next epoch's producer) rewrites it
+                torch.cuda.current_stream().synchronize()
+                for s in self.slots:
+                    s.event = None

@@ -182,6 +182,9 @@ class GraphedTrainStep:
             self._capture(c)
         self._count_tokens_eager(c)
         c.graph.replay()
+        # graph replays update the parameters without touching their autograd version counters: tell weight caches
+        # keyed on those (incremental.IncrementalDecoder) that the weights moved
+        self.model.decoder.weights_epoch = getattr(self.model.decoder, "weights_epoch", 0) + 1
         if self.world > 1:
             torch.cat([g.reshape(-1) for g in c.grads], out=self.static_flat)
             dist.all_reduce(self.static_flat, group=self.group)

@@ -104,7 +104,10 @@ class IncrementalDecoder:
         """Concatenated / operand-form weights in STATIC tensors (captured graphs keep pointing at them);
         refreshed only when a parameter changed."""
         ps = list(self.dec.parameters())
-        version = tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
+        # `weights_epoch` is bumped by engine.GraphedTrainStep after every replay: parameter updates made INSIDE a
+        # captured CUDA graph change neither _version nor data_ptr
+        version = (getattr(self.dec, "weights_epoch", 0),) + tuple(p._version for p in ps) + \
+            tuple(p.data_ptr() for p in ps)
         if version == self.w_version:
             return
         be = self.be

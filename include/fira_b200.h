@@ -93,6 +93,14 @@ int fira_comb_gate_bwd(const void* qk, long ld_qk, const float* vtab, const int*
                        float* d_vtab, long rows, int dim, int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr,
                        uint32_t stream_id, int dtype, void* stream);
 
+/* The same gate with an arbitrary per-row `value` tensor (the stand-alone Combination.forward(query, key, value) /
+ * CombinationLayer.forward of gnn_transformer.py:192-205, combination_layer.py:7-17): q, k, v, out are [rows, dim]. */
+int fira_comb_gate3_fwd(const void* q, const void* k, const void* v, void* out, long rows, int dim, int d_head,
+                        float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, int dtype, void* stream);
+int fira_comb_gate3_bwd(const void* q, const void* k, const void* v, const void* d_out, void* d_q, void* d_k, void* d_v,
+                        long rows, int dim, int d_head, float p_drop, uint64_t seed, const uint64_t* seed_ctr,
+                        uint32_t stream_id, int dtype, void* stream);
+
 /* d[i] = h[i] > 0 ? d[i] : 0  (backward of the FeedForward relu, gnn_transformer.py:172). */
 int fira_relu_bwd(const void* h, void* d, long n, int dtype, void* stream);
 /* out[n] += sum_m w[m] * x[m,n]  (w == NULL -> 1): bias gradients. */

@@ -179,8 +179,9 @@ def main_train():
     dev_set = TransDataset(args, 'valid')
     all_index = json.load(open('all_index'))
     lo, hi = shard_range(len(train_set), RANK, WORLD)               # graphs shard by commit
-    if WORLD > 1:
-        hi = lo + (len(train_set) // WORLD)                         # equal step counts on every rank
+    if WORLD > 1:                                                   # equal step counts on every rank: floor-sized
+        per = len(train_set) // WORLD                               # contiguous shards (never past the end)
+        lo, hi = RANK * per, RANK * per + per
     dev_loader = loader(dev_set, args.batch_size, False)
     model = TransModel(args).to(dev_)
     if os.environ.get("FIRA_ENGINE", "graph") == "graph":

@@ -23,12 +23,14 @@ def _need_cuda():
         pytest.skip("no CUDA device")
 
 
+@pytest.mark.parametrize("golden", ["beam_first16.npz", "beam5_first16.npz"])      # beam 3 (run_model.py:43), beam 5
 @pytest.mark.parametrize("mode", ["full", "incremental", "graph"])
-def test_beam_search_ids_match_reference_test_loop(mode):
+def test_beam_search_ids_match_reference_test_loop(mode, golden):
     """mode: full decoder re-run per step / KV-cached newest row / the same replayed as CUDA graphs
-    (first batch captures, later batches replay)"""
+    (first batch captures, later batches replay); goldens = outputs of the unmodified reference's test() loop
+    (tests/golden/make_golden_beam.py) with beam 3 (the reference default) and beam 5 (BASELINE.json configs[3])"""
     from fira_icse_b200.beam import beam_search, best_sequences
-    gold = np.load(os.path.join(GOLDEN, "beam_first16.npz"))
+    gold = np.load(os.path.join(GOLDEN, golden))
     raw = load_raw_golden()
     vocab = raw["word_vocab"]
     model = copy.deepcopy(seeded_model()).to(DEV).eval()

@@ -171,6 +171,22 @@ def test_empty_and_ragged_inputs(model):
 
 
 # ------------------------------------------------------------------ bf16 throughput mode (tcgen05 GEMMs)
+BF16_LOGP_EPS = 5e-2     # bound on |log p_bf16 - log p_fp32| through 12 post-LN layers of bf16 activations
+
+
+def _head_nll(m, batch):
+    """per-position NLL of model `m` (its precision mode) on `batch` through the public sub-modules"""
+    from fira_icse_b200 import ops
+    sou, tar, attr, mark, ast_change, edge, tar_label, sub_token = batch
+    code, sub = m.encoder(sou, sou != 0, attr, mark, ast_change, edge, sub_token)
+    memory = torch.cat((code, sub), 1)
+    mem_mask = torch.cat((sou != 0, sub_token != 0), 1)
+    dec = m.decoder(tar, memory, mem_mask, tar != 0)
+    return ops.HeadFn.apply(False, m.precision == "bf16", None, memory, dec, mem_mask.to(torch.uint8),
+                            m.shifted_label(tar_label).to(torch.int32).view(-1),
+                            m.out_fc.weight, m.out_fc.bias, *m.copy_net.flat_params())
+
+
 def _cos(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
@@ -208,7 +224,29 @@ def test_bf16_mode_tracks_fp32_mode(model, gold):
     with torch.no_grad():
         ids16 = m(*batch, "dev")
         ids32 = model(*batch, "dev")
-    assert (ids16 == ids32).float().mean().item() > 0.9
+    # argmax ids of the bf16 mode: identical to the fp32 mode wherever the fp32 REFERENCE distribution decides the
+    # position by more than the bf16 mode's own log-probability error; every disagreement must be such a near-tie
+    # (random-initialised weights: rows are near-uniform over 25,020 entries, top-1/top-2 gaps of 1e-3 are common).
+    import fira_oracle as O
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    detail = {}
+    with torch.no_grad():
+        O.forward(sd, *golden_batch(0, n), stage="train", detail=detail)
+    logp = detail["logp"]                                          # fp32 oracle, [n, 30, 25020]
+    bad = torch.nonzero(ids16.cpu() != ids32.cpu())
+    worst_gap = 0.0
+    for i, t in bad.tolist():
+        gap = float(logp[i, t, int(ids32[i, t])] - logp[i, t, int(ids16[i, t])])
+        worst_gap = max(worst_gap, abs(gap))
+        assert abs(gap) <= BF16_LOGP_EPS, f"commit {i} position {t}: bf16 argmax differs beyond a near-tie ({gap:.3e})"
+    print(f"bf16 argmax: {len(bad)} of {ids32.numel()} positions differ, all near-ties (worst fp32 gap {worst_gap:.2e})")
+    # and the per-position NLL of the bf16 mode stays within the same bound of the fp32 reference
+    from fira_icse_b200 import ops
+    with torch.no_grad():
+        nll32 = detail["nll"]
+        _, nll16, _ = _head_nll(m, batch)
+    keep = nll32 != 0
+    assert (nll16.cpu()[keep] - nll32[keep]).abs().max().item() <= BF16_LOGP_EPS
 
 
 def test_bf16_training_reduces_loss(model):

@@ -43,5 +43,18 @@ def test_loss_matches_reference_on_extreme_and_truncated_commits(model):
     assert int(n_tok) == int(ref["mask_sum"])
     assert abs(loss_sum.item() - float(ref["loss_sum"])) <= RTOL * float(ref["loss_sum"])
     np.testing.assert_allclose(np.array(one), ref["loss_per_commit"], rtol=RTOL)
-    # random-initialised weights give near-uniform distributions: allow a near-tie flip, nothing systematic
-    assert (ids != ref["argmax_ids"]).sum() <= 2, "argmax ids differ from the reference"
+    # argmax ids: identical to the reference, except at positions that are TIES at fp32 resolution in the fp32
+    # reference distribution itself (random-initialised weights give near-uniform rows): there the log-probability
+    # of the id picked here must equal the reference's top-1 log-probability to within fp32 round-off of the
+    # 25,020-wide softmax (|logp| ~ 10, one ulp ~ 1e-6)
+    bad = np.argwhere(ids != ref["argmax_ids"])
+    if len(bad):
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        detail = {}
+        with torch.no_grad():
+            O.forward(sd, *[b.cpu() for b in batch], stage="train", detail=detail)
+        logp = detail["logp"]
+        for i, t in bad:
+            gap = float(logp[i, t, int(ref["argmax_ids"][i, t])] - logp[i, t, int(ids[i, t])])
+            assert abs(gap) <= 4e-6, f"commit {i} position {t}: not a tie (log-prob gap {gap:.3e})"
+    assert len(bad) <= 2, "argmax ids differ from the reference at more than two (tied) positions"

@@ -20,7 +20,7 @@ def test_library_exports_every_symbol_the_header_declares():
     for name in protos:
         assert hasattr(handle, name), f"{name} declared in include/fira_b200.h but not exported"
     lib = _lib.lib()
-    assert lib.fira_version() == 1 and lib.fira_built_arch() == 100
+    assert lib.fira_version() == 2 and lib.fira_built_arch() == 100
     out = os.popen(f"nm -D --defined-only {_lib.LIB_PATH}").read()
     exported = {l.split()[-1] for l in out.splitlines() if " T fira_" in l}
     assert exported == set(protos), exported ^ set(protos)     # nothing exported that the header hides

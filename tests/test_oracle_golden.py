@@ -109,3 +109,41 @@ def test_oracle_gradients_match_reference(sd, gold):
             name = k.split("::", 1)[1]
             np.testing.assert_allclose(params[name].grad.numpy(), gold[k], rtol=2e-3,
                                        atol=1e-7 + 2e-4 * float(np.abs(gold[k]).max()))
+
+
+def test_oracle_port_equals_staged_reference_model():
+    """oracle/_ref (the unmodified reference files staged by oracle/make_ref.sh, what bench.py's CPU legs time) and
+    the oracle port evaluate the same loss and argmax ids on real commits with the same weights."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    from fira_testlib import ROOT, golden_batch, reference_args
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "Model.py")):
+        pytest.skip("oracle/_ref not staged (run `sh oracle/make_ref.sh` where /root/reference exists)")
+    code = r"""
+import sys, json, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+from Model import TransModel
+import fira_oracle as O
+from fira_testlib import golden_batch, reference_args
+torch.manual_seed(0)
+m = TransModel(reference_args()); m.eval()
+b = golden_batch(3, 6)
+with torch.no_grad():
+    loss, mask = m(*b, 'train')
+    ids = m(*b, 'dev')
+    sd = {k: v for k, v in m.state_dict().items()}
+    l2, n2 = O.forward(sd, *b, stage='train')
+    ids2 = O.forward(sd, *b, stage='dev')
+print(json.dumps({'ref': float(loss.sum()), 'port': float(l2), 'n': int(mask.sum()), 'n2': int(n2),
+                  'ids_equal': bool(torch.equal(ids, ids2))}))
+""" % (ref_dir, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CUDA_VISIBLE_DEVICES=""),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["n"] == out["n2"] and out["ids_equal"]
+    assert abs(out["ref"] - out["port"]) <= 1e-5 * abs(out["ref"])
