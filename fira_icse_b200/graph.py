@@ -32,6 +32,7 @@ class PackedEdges:
         self.symmetric = bool(symmetric)
         self._t = transpose
         self._rowsum = {}
+        self._rows = {}
 
     @property
     def nnz(self):
@@ -61,6 +62,24 @@ class PackedEdges:
                       n_ast, out.data_ptr(), _stream())
             self._rowsum[key] = out
         return self._rowsum[key]
+
+    def rows_csr(self, n_code, n_sub, n_ast):
+        """The same adjacency as a CSR in BUFFER order for the fused GCN layer kernel (fira_gcn_layer_fwd/bwd):
+        rowptr indexed by the segment-major row of the node buffer, col = buffer rows.  -> (rowptr, col, val)."""
+        key = (n_code, n_sub, n_ast)
+        if key not in self._rows:
+            assert n_code + n_sub + n_ast == self.N
+            R = self.B * self.N
+            dev = self.device
+            counts = torch.empty(R, dtype=torch.int32, device=dev)
+            rowptr = torch.empty(R + 1, dtype=torch.int32, device=dev)
+            col = torch.empty(max(self.col.numel(), 1), dtype=torch.int32, device=dev)
+            val = torch.empty(max(self.col.numel(), 1), dtype=torch.float32, device=dev)
+            _lib.call("fira_csr_to_rows", self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), self.B,
+                      n_code, n_sub, n_ast, counts.data_ptr(), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                      _stream())
+            self._rows[key] = (rowptr, col, val)
+        return self._rows[key]
 
     # ------------------------------------------------------------------ constructors
     @staticmethod

@@ -15,6 +15,8 @@ Buffer conventions
     (kills the per-layer torch.cat/slice of gnn_transformer.py:58,86); `Xc` holds the code rows a
     Combination reads, `Gin` holds every row a GCN layer reads.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -258,7 +260,9 @@ def _prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2):
     gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
     for w in (Wqk, Wo, Wc):
         pr.w(w)                                                    # bf16 operand copies (no-op in fp32 mode)
-    return Wqk, bqk, Vtab, Wc, c1
+    # the fused GCN backward multiplies by Wc itself ([out, in] read as K = out): its B operand is Wc^T stored K-major
+    WcT16 = Wc.t().contiguous().to(torch.bfloat16) if pr.bf16 else None
+    return Wqk, bqk, Vtab, Wc, c1, WcT16
 
 
 def prefetch_decoder(bf16, lp, device):
@@ -341,7 +345,11 @@ class EncoderFn(torch.autograd.Function):
         Gin = pr.empty((R, D), dev)
         call("fira_embed_nodes_fwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(emb), _ptr(ast_emb),
              _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
-        rs = edges.rowsum(n_code, n_sub, n_ast)
+        # bf16 mode: the GCN layer is ONE fused kernel (gather -> tcgen05 -> LayerNorm epilogue, csrc/gcn_fused.cu);
+        # FIRA_GCN_FUSED=0 keeps the three-launch sequence (scatter, GEMM, LayerNorm) for A/B measurements
+        fused = pr.bf16 and os.environ.get("FIRA_GCN_FUSED", "0") != "0"      # TODO default on once validated on the GPU
+        rs = None if fused else edges.rowsum(n_code, n_sub, n_ast)
+        erows = edges.rows_csr(n_code, n_sub, n_ast) if fused else None
         saved = []
         # weight-only work of ALL layers goes to the side stream, layer 0 first; the main stream waits for
         # layer i's event right before it needs it, so only the first layer's ~8 tiny launches are exposed
@@ -358,7 +366,7 @@ class EncoderFn(torch.autograd.Function):
             Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
             sid = cfg["stream_base"] + i * 8
             torch.cuda.current_stream().wait_event(events[i])
-            Wqk, bqk, Vtab, Wc, c1 = preps[i]
+            Wqk, bqk, Vtab, Wc, c1, WcT16 = preps[i]
             # ---- Combination (gnn_transformer.py:192-205, combination_layer.py:7-17)
             QK = pr.linear(Xc, Wqk, bqk)                               # [Mc, 512] = [q | k]
             Cd = pr.empty((Mc, D), dev)
@@ -367,14 +375,22 @@ class EncoderFn(torch.autograd.Function):
             Zc = pr.linear(Cd, Wo, bo)
             st_c = pr.ln_fwd(Zc, Xc, clw, clb, Gin, Gin, Mc, Mc, p_comb, seed, sid + 1)   # -> Gin[:Mc]
             # ---- GCN (gnn_transformer.py:74-86)
-            G = pr.empty((R, D), dev)
-            call("fira_gcn_aggregate", _ptr(edges.rowptr), _ptr(edges.col), _ptr(edges.val), _ptr(Gin), None,
-                 _ptr(G), B, n_code, n_sub, n_ast, D, pr.code, st)
-            Z = pr.linear(G, Wc, b2, rs=rs, rc=c1)
             Xc_n = pr.empty((Mc, D), dev)
             Gin_n = pr.empty((R, D), dev)
-            st_g = pr.ln_fwd(Z, Gin, glw, glb, Xc_n, Gin_n, Mc, R, p_gcn, seed, sid + 2)
-            saved.append((Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1))
+            if fused:
+                G = None
+                Z = pr.empty((R, D), dev)
+                st_g = torch.empty((2, R), **f32)
+                call("fira_gcn_layer_fwd", _ptr(erows[0]), _ptr(erows[1]), _ptr(erows[2]), _ptr(Gin), _ptr(pr.w(Wc)),
+                     _ptr(b2), _ptr(c1), _ptr(glw), _ptr(glb), _ptr(Z), _ptr(Xc_n), _ptr(Gin_n), Mc, _ptr(st_g),
+                     _ptr(st_g, R), R, D, float(p_gcn), seed, _ptr(pr.seed_ctr), sid + 2, st)
+            else:
+                G = pr.empty((R, D), dev)
+                call("fira_gcn_aggregate", _ptr(edges.rowptr), _ptr(edges.col), _ptr(edges.val), _ptr(Gin), None,
+                     _ptr(G), B, n_code, n_sub, n_ast, D, pr.code, st)
+                Z = pr.linear(G, Wc, b2, rs=rs, rc=c1)
+                st_g = pr.ln_fwd(Z, Gin, glw, glb, Xc_n, Gin_n, Mc, R, p_gcn, seed, sid + 2)
+            saved.append((Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1, WcT16))
             Xc, Gin = Xc_n, Gin_n
         memory = pr.empty((B, n_code + n_sub, D), dev)
         call("fira_pack_memory", _ptr(Xc), _ptr(Gin), _ptr(memory), B, n_code, n_sub, D, pr.code, st)
@@ -382,13 +398,13 @@ class EncoderFn(torch.autograd.Function):
 
         ctx.saved = saved
         ctx.wcache = pr.wcache
-        ctx.misc = (cfg, sou, mark, ast_change, sub_token, edges, rs, B, n_code, n_sub, n_ast, p_comb, p_gcn)
+        ctx.misc = (cfg, sou, mark, ast_change, sub_token, edges, rs, B, n_code, n_sub, n_ast, p_comb, p_gcn, fused)
         ctx.save_for_backward(emb, ast_emb, mark_emb, *lp)
         return memory
 
     @staticmethod
     def backward(ctx, d_mem):
-        cfg, sou, mark, ast_change, sub_token, edges, rs, B, n_code, n_sub, n_ast, p_comb, p_gcn = ctx.misc
+        cfg, sou, mark, ast_change, sub_token, edges, rs, B, n_code, n_sub, n_ast, p_comb, p_gcn, fused = ctx.misc
         emb, ast_emb, mark_emb, *lp = ctx.saved_tensors
         N = n_code + n_sub + n_ast
         R, Mc = B * N, B * n_code
@@ -399,6 +415,7 @@ class EncoderFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
         et = edges.t()
+        etrows = et.rows_csr(n_code, n_sub, n_ast) if fused else None
         d_mem = d_mem.contiguous().to(pr.tdt)
         dXc = pr.empty((Mc, D), dev)
         dGin = pr.empty((R, D), dev)
@@ -408,14 +425,25 @@ class EncoderFn(torch.autograd.Function):
         fork = Fork(dev)
         for i in reversed(range(L)):
             Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
-            Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1 = ctx.saved[i]
+            Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1, WcT16 = ctx.saved[i]
             sid = cfg["stream_base"] + i * 8
             # ---- GCN backward
             dZ, dRes, d_glw, d_glb = pr.ln_bwd(dXc, dGin, Mc, Z, Gin, st_g, glw, R, p_gcn, seed, sid + 2)
+            dGin_i = pr.empty((R, D), dev)
+            if fused:
+                # one kernel: AdZ = A^T dZ (kept for the weight gradients), dGin_i = AdZ Wc + dRes
+                AdZ = pr.empty((R, D), dev)
+                call("fira_gcn_layer_bwd", _ptr(etrows[0]), _ptr(etrows[1]), _ptr(etrows[2]), _ptr(dZ), _ptr(WcT16),
+                     _ptr(dRes), _ptr(AdZ), _ptr(dGin_i), R, D, st)
             with fork(dZ, G, rs, W1, W2, b1):
                 d_b2 = colsum(dZ, D, R, D)
-                d_c1 = colsum(dZ, D, R, D, weight=rs)
-                dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
+                if fused:                       # dZ^T (A H) = (A^T dZ)^T H ;  sum_i rowsum(A)_i dZ_i = colsum(A^T dZ)
+                    fork.keep.append(AdZ)
+                    d_c1 = colsum(AdZ, D, R, D)
+                    dWc = pr.linear_dw(AdZ, D, Gin, D, R, D, D)
+                else:
+                    d_c1 = colsum(dZ, D, R, D, weight=rs)
+                    dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
                 d_W2 = torch.empty((D, D), **f32)       # dWc W1^T + d_c1 b1^T
                 gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=1)
                 d_W1 = torch.empty((D, D), **f32)       # W2^T dWc
@@ -423,10 +451,10 @@ class EncoderFn(torch.autograd.Function):
                 d_b1 = torch.empty((D,), **f32)         # W2^T d_c1
                 gemm_raw(_ptr(W2), D, 0, _ptr(d_c1), 1, 0, _ptr(d_b1), 1, D, 1, D, splits=1)
                 fork.keep.extend((dWc, d_c1))
-            dG = pr.linear_dx(dZ, D, Wc, R)
-            dGin_i = pr.empty((R, D), dev)
-            call("fira_gcn_aggregate", _ptr(et.rowptr), _ptr(et.col), _ptr(et.val), _ptr(dG), _ptr(dRes),
-                 _ptr(dGin_i), B, n_code, n_sub, n_ast, D, pr.code, st)
+            if not fused:
+                dG = pr.linear_dx(dZ, D, Wc, R)
+                call("fira_gcn_aggregate", _ptr(et.rowptr), _ptr(et.col), _ptr(et.val), _ptr(dG), _ptr(dRes),
+                     _ptr(dGin_i), B, n_code, n_sub, n_ast, D, pr.code, st)
             # ---- Combination backward (rows < Mc of dGin_i are d(comb output))
             dXc_n = pr.empty((Mc, D), dev)
             dZc, _, d_clw, d_clb = pr.ln_bwd(dGin_i, dGin_i, Mc, Zc, Xc, st_c, clw, Mc, p_comb, seed, sid + 1,

@@ -125,6 +125,25 @@ int fira_csr_rowsum(const int* rowptr, const float* val, int B, int n_code, int 
 int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, const void* x, const void* addend,
                        void* y, int B, int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream);
 
+/* ---- fused GCN layer, bf16 throughput mode (gnn_transformer.py:74-86 as ONE kernel per direction): gather the
+ *      neighbour rows into the shared-memory A tile -> tcgen05.mma with the merged weight -> epilogue out of TMEM.
+ *      The CSR is in BUFFER order: rowptr_rows[r] indexes the rows of the node buffer, col_rows are buffer rows
+ *      (fira_csr_to_rows converts the (graph, node)-ordered CSR; counts is an int32[rows] workspace).
+ *   fwd:  z = (A h) w_merged^T + rowsum(A) (x) c1 + bias ;  out = LN(dropout(z) + h)   (w_merged = fc2.W fc1.W [out,in]
+ *         bf16, c1 = fc2.W fc1.b, bias = fc2.b; rows < split -> outA[row], the others -> outB[row]; mean/rstd for
+ *         fira_ln_residual_bwd; the dropout mask is the one fira_ln_residual_fwd/bwd draw for (seed, stream_id)).
+ *   bwd:  agg_dz = A^T dz (kept: d(w_merged) = agg_dz^T h, d(c1) = colsum(agg_dz)) ;  d_h = agg_dz w_merged + d_resid
+ *         (w_merged_t = w_merged^T as a row-major [in,out] bf16 matrix; rowptr/col/val of A^T, = A when symmetric). */
+int fira_csr_to_rows(const int* rowptr, const int* col, const float* val, int B, int n_code, int n_sub, int n_ast,
+                     int* counts, int* rowptr_rows, int* col_rows, float* val_rows, void* stream);
+int fira_gcn_layer_fwd(const int* rowptr_rows, const int* col_rows, const float* val_rows, const void* h,
+                       const void* w_merged, const float* bias, const float* c1, const float* gamma, const float* beta,
+                       void* z, void* outA, void* outB, long split, float* mean, float* rstd, long rows, int dim,
+                       float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t stream_id, void* stream);
+int fira_gcn_layer_bwd(const int* rowptr_rows_t, const int* col_rows_t, const float* val_rows_t, const void* d_z,
+                       const void* w_merged_t, const void* d_resid, void* agg_dz, void* d_h, long rows, int dim,
+                       void* stream);
+
 /* ---- attention core (gnn_transformer.py:144-156); stats = (row max, row sum) [B,H,Lq,2];
  *      backward also takes the forward output `ctx` (same layout as d_ctx): delta = dO . O. */
 int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
