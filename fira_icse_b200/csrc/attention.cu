@@ -11,10 +11,28 @@
 // Forward saves (row max, row sum); backward recomputes P from them, gets delta = rowsum(P * dP) as
 // dO . O (so keys can be processed in chunks of 64 with a small shared-memory footprint, 5 CTAs/SM)
 // and writes zero gradients for the masked keys.
+#include <stdlib.h>
 #include "common.cuh"
 #include "fira_b200.h"
 
+// tcgen05 path of the bf16 mode (attention_tc.cu)
+int fira_attn_tc_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                     const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
+                     int Lk, void* stream);
+int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                     const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
+                     const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
+                     int Lq, int Lk, void* stream);
+bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv);
+
 namespace {
+
+// bf16 activations go to the tensor-core kernels unless FIRA_ATTN_TC=0 (A/B runs against the FFMA kernels below)
+bool use_tc(int dtype, int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv) {
+  if (dtype != FIRA_BF16 || !fira_attn_tc_eligible(B, H, Lq, Lk, d_head, ldk, ldv)) return false;
+  const char* e = getenv("FIRA_ATTN_TC");
+  return e ? atoi(e) != 0 : false;      // TODO default on once validated on the GPU
+}
 
 constexpr int DH = 32;           // head dim (256 / 8)
 constexpr int KPAD = DH + 1;     // conflict-free column reads of K/V tiles
@@ -318,6 +336,8 @@ int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* 
   if ((rc = check_layout("attn_fwd", q, ldq, dtype)) || (rc = check_layout("attn_fwd", k, ldk, dtype)) ||
       (rc = check_layout("attn_fwd", v, ldv, dtype)))
     return rc;
+  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv))
+    return fira_attn_tc_fwd(q, ldq, k, ldk, v, ldv, key_mask, causal, ctx, ldo, stats, B, H, Lq, Lk, stream);
   AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = fwd_smem(Lq, Lk);
   if (dtype == FIRA_F32) {
@@ -343,6 +363,9 @@ int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* 
       (rc = check_layout("attn_bwd", v, ldv, dtype)) || (rc = check_layout("attn_bwd", ctx, ldo, dtype)) ||
       (rc = check_layout("attn_bwd", d_ctx, ldo, dtype)))
     return rc;
+  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv) && (lddk % 8) == 0 && (lddv % 8) == 0 && (lddq % 8) == 0)
+    return fira_attn_tc_bwd(q, ldq, k, ldk, v, ldv, key_mask, causal, ctx, d_ctx, ldo, stats, dq, lddq, dk, lddk, dv, lddv,
+                            B, H, Lq, Lk, stream);
   AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = bwd_smem(Lq, Lk);
   if (dtype == FIRA_F32) {
