@@ -176,4 +176,135 @@ int fira_host_gather_batch(const int* sou, const int* tar, const int* mark, cons
   return FIRA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ per-commit packing
+// SURVEY.md 8f rank 4 / Dataset.py:80-94: the reference pads every commit to 210 / 160 / 280 nodes.  Padding nodes are
+// isolated (self loop only, Dataset.py:271-275), masked in cross-attention and in the copy softmax, so they never reach
+// a real row or the loss.  The packed batch keeps, per commit and segment, only the positions up to the last non-zero
+// id ("used" length); node rows are segment-major and RAGGED: [code rows of commit 0, 1, ... | pad | sub-token rows ...
+// | pad | AST/edit rows ... | pad], each segment padded to a caller-chosen bucket size with empty rows.
+int fira_host_packed_dims(const int* sou, const int* sub_token, const int* ast_change, const unsigned char* deg,
+                          const long* index, int batch, int diff_len, int sub_len, int ast_change_len, int* dims) {
+  FIRA_CHECK_ARG(sou && sub_token && ast_change && deg && index && dims && batch > 0, FIRA_ERR_ARG,
+                 "fira_host_packed_dims: null pointer or empty batch");
+  const int n0 = diff_len, n1 = sub_len, n2 = ast_change_len, N = n0 + n1 + n2;
+  auto used = [](const int* row, int len) { int u = 0; for (int j = 0; j < len; ++j) if (row[j] != 0) u = j + 1; return u; };
+  long rc = 0, rs = 0, ra = 0, nnz = 0;
+  int smax = 0;
+  for (int b = 0; b < batch; ++b) {
+    const long i = index[b];
+    const int uc = used(sou + i * n0, n0), us = used(sub_token + i * n1, n1), ua = used(ast_change + i * n2, n2);
+    rc += uc; rs += us; ra += ua;
+    smax = std::max(smax, uc + us);
+    const unsigned char* d = deg + i * N;
+    for (int j = 0; j < uc; ++j) nnz += d[j];
+    for (int j = 0; j < us; ++j) nnz += d[n0 + j];
+    for (int j = 0; j < ua; ++j) nnz += d[n0 + n1 + j];
+  }
+  dims[0] = (int)rc; dims[1] = (int)rs; dims[2] = (int)ra; dims[3] = smax; dims[4] = (int)nnz;
+  return FIRA_OK;
+}
+
+int fira_host_gather_packed(const int* sou, const int* tar, const int* mark, const int* ast_change,
+                            const int* tar_label, const int* sub_token, const unsigned char* deg, const short* col,
+                            const double* val, const long* edge_ptr, const long* index, int batch, int diff_len,
+                            int sub_len, int ast_change_len, int msg_len, int vocab_size, const int* pad_dims,
+                            int* o_code, int* o_mark, int* o_pos, int* o_sub, int* o_ast, int* o_off, int* o_ranges,
+                            unsigned char* o_mem_mask, int* o_tar, int* o_label, unsigned char* o_tar_mask,
+                            int* o_rowptr, int* o_col, float* o_val, long edge_cap, int* nnz_out) {
+  FIRA_CHECK_ARG(batch > 0 && diff_len > 0 && msg_len > 0, FIRA_ERR_SHAPE, "fira_host_gather_packed: bad shape");
+  FIRA_CHECK_ARG(sou && tar && mark && ast_change && tar_label && sub_token && deg && col && val && edge_ptr && index &&
+                     pad_dims && o_code && o_mark && o_pos && o_sub && o_ast && o_off && o_ranges && o_mem_mask &&
+                     o_tar && o_label && o_tar_mask && o_rowptr && o_col && o_val && nnz_out,
+                 FIRA_ERR_ARG, "fira_host_gather_packed: null pointer");
+  const int n0 = diff_len, n1 = sub_len, n2 = ast_change_len, N = n0 + n1 + n2, V = vocab_size;
+  const int Rc = pad_dims[0], Rs = pad_dims[1], Ra = pad_dims[2], S = pad_dims[3];
+  auto used = [](const int* row, int len) { int u = 0; for (int j = 0; j < len; ++j) if (row[j] != 0) u = j + 1; return u; };
+  int* off_c = o_off; int* off_s = o_off + (batch + 1); int* off_a = o_off + 2 * (batch + 1);
+  off_c[0] = off_s[0] = off_a[0] = 0;
+  for (int b = 0; b < batch; ++b) {
+    const long i = index[b];
+    off_c[b + 1] = off_c[b] + used(sou + i * n0, n0);
+    off_s[b + 1] = off_s[b] + used(sub_token + i * n1, n1);
+    off_a[b + 1] = off_a[b] + used(ast_change + i * n2, n2);
+  }
+  FIRA_CHECK_ARG(off_c[batch] <= Rc && off_s[batch] <= Rs && off_a[batch] <= Ra, FIRA_ERR_SHAPE,
+                 "fira_host_gather_packed: batch needs (%d, %d, %d) rows, buffers hold (%d, %d, %d)", off_c[batch],
+                 off_s[batch], off_a[batch], Rc, Rs, Ra);
+  // ---- node ids (int32), padding rows of each segment = id 0
+  memset(o_code, 0, sizeof(int) * Rc); memset(o_mark, 0, sizeof(int) * Rc); memset(o_pos, 0, sizeof(int) * Rc);
+  memset(o_sub, 0, sizeof(int) * Rs); memset(o_ast, 0, sizeof(int) * Ra);
+  memset(o_mem_mask, 0, (size_t)batch * S);
+  for (int b = 0; b < batch; ++b) {
+    const long i = index[b];
+    const int uc = off_c[b + 1] - off_c[b], us = off_s[b + 1] - off_s[b], ua = off_a[b + 1] - off_a[b];
+    FIRA_CHECK_ARG(uc + us <= S, FIRA_ERR_SHAPE, "fira_host_gather_packed: commit %ld has %d memory rows, S = %d", i,
+                   uc + us, S);
+    for (int j = 0; j < uc; ++j) {
+      o_code[off_c[b] + j] = sou[i * n0 + j];
+      o_mark[off_c[b] + j] = mark[i * n0 + j];
+      o_pos[off_c[b] + j] = j;
+      o_mem_mask[(long)b * S + j] = sou[i * n0 + j] != 0;          // an interior zero id stays masked (Model.py:42)
+    }
+    for (int j = 0; j < us; ++j) {
+      o_sub[off_s[b] + j] = sub_token[i * n1 + j];
+      o_mem_mask[(long)b * S + uc + j] = sub_token[i * n1 + j] != 0;
+    }
+    for (int j = 0; j < ua; ++j) o_ast[off_a[b] + j] = ast_change[i * n2 + j];
+    o_ranges[4 * b + 0] = off_c[b]; o_ranges[4 * b + 1] = uc;
+    o_ranges[4 * b + 2] = Rc + off_s[b]; o_ranges[4 * b + 3] = us;
+    // decoder input, shifted labels (Model.py:71-79) with copy labels renumbered to the commit's own memory rows:
+    // code position s -> V + s, sub-token k -> V + uc + k; a label on a padded source position (p = 0 in the
+    // reference: masked, Model.py:61) -> V + S, which head_fwd_kernel treats as "beyond the source" (p = 0 as well)
+    for (int t = 0; t < msg_len; ++t) {
+      const int tk = tar[i * msg_len + t];
+      o_tar[(long)b * msg_len + t] = tk;
+      o_tar_mask[(long)b * msg_len + t] = tk != 0;
+      long l = t + 1 < msg_len ? tar_label[i * msg_len + t + 1] : 0;
+      if (l >= V) {
+        const long s = l - V;
+        if (s < n0) l = s < uc ? V + s : (long)V + S;
+        else { const long k = s - n0; l = k < us ? V + uc + k : (long)V + S; }
+      }
+      o_label[(long)b * msg_len + t] = (int)l;
+    }
+  }
+  // ---- buffer-order CSR with GLOBAL column ids
+  long nnz = 0;
+  o_rowptr[0] = 0;
+  const int seg_lo[3] = {0, n0, n0 + n1};
+  const int seg_base[3] = {0, Rc, Rc + Rs};
+  const int seg_rows[3] = {Rc, Rs, Ra};
+  const int* seg_off[3] = {off_c, off_s, off_a};
+  for (int sgm = 0; sgm < 3; ++sgm) {
+    for (int b = 0; b < batch; ++b) {
+      const long i = index[b];
+      const unsigned char* d = deg + i * N;
+      long e = edge_ptr[i];
+      for (int r = 0; r < seg_lo[sgm]; ++r) e += d[r];
+      const int u = seg_off[sgm][b + 1] - seg_off[sgm][b];
+      const int ucs[3] = {off_c[b + 1] - off_c[b], off_s[b + 1] - off_s[b], off_a[b + 1] - off_a[b]};
+      for (int j = 0; j < u; ++j) {
+        const int dr = d[seg_lo[sgm] + j];
+        FIRA_CHECK_ARG(nnz + dr <= edge_cap, FIRA_ERR_SHAPE, "fira_host_gather_packed: more than %ld edges", edge_cap);
+        for (int k = 0; k < dr; ++k) {
+          const int c = col[e + k];
+          const int cs = c < n0 ? 0 : (c < n0 + n1 ? 1 : 2);
+          const int cj = c - seg_lo[cs];
+          FIRA_CHECK_ARG(cj < ucs[cs], FIRA_ERR_ARG,
+                         "fira_host_gather_packed: commit %ld node %d has a neighbour (%d) inside the dropped padding", i,
+                         seg_lo[sgm] + j, c);
+          o_col[nnz + k] = seg_base[cs] + seg_off[cs][b] + cj;
+          o_val[nnz + k] = (float)val[e + k];
+        }
+        nnz += dr;
+        e += dr;
+        o_rowptr[seg_base[sgm] + seg_off[sgm][b] + j + 1] = (int)nnz;
+      }
+    }
+    for (int r = seg_off[sgm][batch]; r < seg_rows[sgm]; ++r) o_rowptr[seg_base[sgm] + r + 1] = (int)nnz;   // empty pad rows
+  }
+  *nnz_out = (int)nnz;
+  return FIRA_OK;
+}
+
 }  // extern "C"

@@ -212,6 +212,26 @@ int fira_host_gather_batch(const int* sou, const int* tar, const int* mark, cons
                            long* o_sou, long* o_tar, long* o_mark, long* o_ast_change, long* o_tar_label,
                            long* o_sub_token, int* o_rowptr, int* o_col, float* o_val, long edge_cap, int* nnz_out);
 
+/* fira_host_packed_dims / fira_host_gather_packed: the PER-COMMIT packed batch (replaces the
+ *   fixed 210/160/280 padding of Dataset.py:80-94).  Per commit and segment only the positions up to the last non-zero
+ *   id are kept; node rows are segment-major and ragged: [code rows of all commits | pad][sub-token rows | pad]
+ *   [AST/edit rows | pad].  packed_dims -> dims[5] = {code rows, sub rows, AST rows, max memory rows of a commit, nnz}.
+ *   gather_packed: pad_dims[4] = {Rc, Rs, Ra, S} buffer sizes (>= dims, bucketed by the caller); writes int32 node ids
+ *   (o_code, o_mark, o_pos = position in the commit for the positional encoding; o_sub; o_ast), o_off[3][batch+1]
+ *   (row offsets of each commit inside its segment), o_ranges[batch][4] = {first code row, code rows, first sub row
+ *   (global), sub rows}, o_mem_mask[batch][S], the decoder input o_tar[batch][msg_len] + o_tar_mask, the SHIFTED labels
+ *   (Model.py:71-79) with copy labels renumbered to the commit's own memory rows (V + m), and the adjacency as a CSR in
+ *   buffer order with global column ids (what fira_gcn_layer_fwd / fira_gcn_aggregate(B=1) consume). */
+int fira_host_packed_dims(const int* sou, const int* sub_token, const int* ast_change, const unsigned char* deg,
+                          const long* index, int batch, int diff_len, int sub_len, int ast_change_len, int* dims);
+int fira_host_gather_packed(const int* sou, const int* tar, const int* mark, const int* ast_change,
+                            const int* tar_label, const int* sub_token, const unsigned char* deg, const short* col,
+                            const double* val, const long* edge_ptr, const long* index, int batch, int diff_len,
+                            int sub_len, int ast_change_len, int msg_len, int vocab_size, const int* pad_dims,
+                            int* o_code, int* o_mark, int* o_pos, int* o_sub, int* o_ast, int* o_off, int* o_ranges,
+                            unsigned char* o_mem_mask, int* o_tar, int* o_label, unsigned char* o_tar_mask,
+                            int* o_rowptr, int* o_col, float* o_val, long edge_cap, int* nnz_out);
+
 #ifdef __cplusplus
 }
 #endif
