@@ -17,19 +17,19 @@
 
 // tcgen05 path of the bf16 mode (attention_tc.cu)
 int fira_attn_tc_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                     const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
-                     int Lk, void* stream);
+                     const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, void* ctx, long ldo,
+                     float* stats, int B, int H, int Lq, int Lk, void* stream);
 int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                     const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
-                     const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
-                     int Lq, int Lk, void* stream);
-bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv);
+                     const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, const void* ctx,
+                     const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv,
+                     long lddv, int B, int H, int Lq, int Lk, void* stream);
+bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges);
 
 namespace {
 
 // bf16 activations go to the tensor-core kernels unless FIRA_ATTN_TC=0 (A/B runs against the FFMA kernels below)
-bool use_tc(int dtype, int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv) {
-  if (dtype != FIRA_BF16 || !fira_attn_tc_eligible(B, H, Lq, Lk, d_head, ldk, ldv)) return false;
+bool use_tc(int dtype, int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges = false) {
+  if (dtype != FIRA_BF16 || !fira_attn_tc_eligible(B, H, Lq, Lk, d_head, ldk, ldv, ranges)) return false;
   const char* e = getenv("FIRA_ATTN_TC");
   return e ? atoi(e) != 0 : false;      // TODO default on once validated on the GPU
 }
@@ -46,7 +46,8 @@ struct AttnArgs {
   const void* q; long ldq;       // row (b*Lq + t), head h at column h*32
   const void* k; long ldk;       // row (b*Lk + s)
   const void* v; long ldv;
-  const unsigned char* key_mask; // [B, Lk], 1 = attend
+  const unsigned char* key_mask; // [B, Lk], 1 = attend (may be NULL with ranges: all keys valid)
+  const int* ranges;             // NULL, or [B][4] = {first row, rows, first row, rows} of k / v (packed batches)
   int causal;
   int B, H, Lq, Lk;
   float scale;
@@ -79,20 +80,23 @@ __device__ __forceinline__ void load_rows(float* dst, const T* src, long ld, con
 // causal (self-attention, Lk = 30): no compaction -- a row whose every permitted key is padding must stay
 // uniform over ALL keys like the reference, so padding is handled by the score mask instead.
 __device__ __forceinline__ void compact_keys(const unsigned char* km, int Lk, int causal, int* kidx, int* nv_out,
-                                             int* filled) {
+                                             int* filled, const int* rg = nullptr) {
+  // rg != NULL (packed batches): key position m of the commit lives in global row
+  //   m < rg[1] ? rg[0] + m : rg[2] + (m - rg[1]),   m < rg[1] + rg[3];   kidx then holds GLOBAL rows
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
+    const int L = rg ? rg[1] + rg[3] : Lk;
     int n = 0;
-    for (int s0 = 0; s0 < Lk && !causal; s0 += 32) {
+    for (int s0 = 0; s0 < L && !causal; s0 += 32) {
       const int s = s0 + lane;
-      const bool ok = s < Lk && km[s] != 0;
+      const bool ok = s < L && (km == nullptr || km[s] != 0);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) kidx[n + __popc(bal & ((1u << lane) - 1u))] = s;
+      if (ok) kidx[n + __popc(bal & ((1u << lane) - 1u))] = rg ? (s < rg[1] ? rg[0] + s : rg[2] + (s - rg[1])) : s;
       n += __popc(bal);
     }
     if (n == 0) {
-      for (int s = lane; s < Lk; s += 32) kidx[s] = s;
-      n = Lk;
+      for (int s = lane; s < L; s += 32) kidx[s] = rg ? (s < rg[1] ? rg[0] + s : rg[2] + (s - rg[1])) : s;
+      n = L;
       if (lane == 0) *filled = causal ? 0 : 1;
     } else if (lane == 0) *filled = 0;
     if (lane == 0) *nv_out = n;
@@ -117,8 +121,10 @@ __global__ void __launch_bounds__(NTHR) attn_fwd_kernel(AttnArgs a, T* __restric
   float* Qs = Vs + KC * KPAD;                // [Lq][KPAD]
   float* Ps = Qs + a.Lq * KPAD;              // [NWARPS][2][KC]
   int* kidx = reinterpret_cast<int*>(Ps + NWARPS * 2 * KC);   // [Lk]
-  const unsigned char* km = a.key_mask + (long)b * a.Lk;
-  compact_keys(km, a.Lk, a.causal, kidx, &nv_s, &filled_s);
+  const unsigned char* km = a.key_mask ? a.key_mask + (long)b * a.Lk : nullptr;
+  const int* rg = a.ranges ? a.ranges + 4 * b : nullptr;
+  const long kvb = rg ? 0 : (long)b * a.Lk;                    // with ranges kidx holds global rows
+  compact_keys(km, a.Lk, a.causal, kidx, &nv_s, &filled_s, rg);
   const int nv = nv_s;
   const bool filled = filled_s != 0;
   load_rows(Qs, (const T*)a.q + (long)b * a.Lq * a.ldq + h * DH, a.ldq, nullptr, 0, a.Lq);
@@ -131,8 +137,8 @@ __global__ void __launch_bounds__(NTHR) attn_fwd_kernel(AttnArgs a, T* __restric
   for (int c0 = 0; c0 < nv; c0 += KC) {
     const int nc = min(KC, nv - c0);
     __syncthreads();                                       // previous chunk consumed; Qs visible
-    load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, c0, nc);
-    load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, c0, nc);
+    load_rows(Ks, (const T*)a.k + kvb * a.ldk + h * DH, a.ldk, kidx, c0, nc);
+    load_rows(Vs, (const T*)a.v + kvb * a.ldv + h * DH, a.ldv, kidx, c0, nc);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < PAIRS_MAX; ++i) {
@@ -208,8 +214,10 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
   float* Pm = Os + a.Lq * KPAD;              // [Lq][PP]    P
   float* Sm = Pm + a.Lq * PP;                // [Lq][PP]    dS
   int* kidx = reinterpret_cast<int*>(Sm + a.Lq * PP);   // [Lk]
-  const unsigned char* km = a.key_mask + (long)b * a.Lk;
-  compact_keys(km, a.Lk, a.causal, kidx, &nv_s, &filled_s);
+  const unsigned char* km = a.key_mask ? a.key_mask + (long)b * a.Lk : nullptr;
+  const int* rg = a.ranges ? a.ranges + 4 * b : nullptr;
+  const long kvb = rg ? 0 : (long)b * a.Lk;
+  compact_keys(km, a.Lk, a.causal, kidx, &nv_s, &filled_s, rg);
   const int nv = nv_s;
   const bool filled = filled_s != 0;
   // delta_t = dO_t . O_t  (== sum_s P dP), row statistics
@@ -233,8 +241,8 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
   for (int c0 = 0; c0 < nv; c0 += KCB) {
     const int nc = min(KCB, nv - c0);
     __syncthreads();                                     // previous chunk fully consumed (and Qs loaded)
-    load_rows(Ks, (const T*)a.k + (long)b * a.Lk * a.ldk + h * DH, a.ldk, kidx, c0, nc);
-    load_rows(Vs, (const T*)a.v + (long)b * a.Lk * a.ldv + h * DH, a.ldv, kidx, c0, nc);
+    load_rows(Ks, (const T*)a.k + kvb * a.ldk + h * DH, a.ldk, kidx, c0, nc);
+    load_rows(Vs, (const T*)a.v + kvb * a.ldv + h * DH, a.ldv, kidx, c0, nc);
     __syncthreads();
     // ---- phase A: P, dS for the warp's query rows; dQ accumulation
 #pragma unroll
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
         gk = fmaf(Sm[t * PP + j], Qs[t * KPAD + lane], gk);
         gv = fmaf(Pm[t * PP + j], Os[t * KPAD + lane], gv);
       }
-      const long row = (long)b * a.Lk + kidx[c0 + j];
+      const long row = kvb + kidx[c0 + j];
       Act<T>::st(dk + row * lddk + h * DH + lane, gk * a.scale);
       Act<T>::st(dv + row * lddv + h * DH + lane, gv);
     }
@@ -280,10 +288,11 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
     if (t < a.Lq) Act<T>::st(dq + ((long)b * a.Lq + t) * lddq + h * DH + lane, dqa[i] * a.scale);
   }
   // masked keys receive exactly zero gradient
-  if (!filled && !a.causal) {
-    for (int s = warp; s < a.Lk; s += NWARPS) {
+  if (!filled && !a.causal && km) {
+    const int L = rg ? rg[1] + rg[3] : a.Lk;
+    for (int s = warp; s < L; s += NWARPS) {
       if (km[s] == 0) {
-        const long row = (long)b * a.Lk + s;
+        const long row = rg ? (s < rg[1] ? rg[0] + s : rg[2] + (s - rg[1])) : (long)b * a.Lk + s;
         Act<T>::st(dk + row * lddk + h * DH + lane, 0.f);
         Act<T>::st(dv + row * lddv + h * DH + lane, 0.f);
       }
@@ -323,22 +332,23 @@ int check_layout(const char* name, const void* p, long ld, int dtype) {
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                  const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
-                  int Lk, int d_head, int dtype, void* stream) {
+int attn_fwd_impl(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                  const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, void* ctx, long ldo,
+                  float* stats, int B, int H, int Lq, int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_fwd: d_head %d != 32", d_head);
   FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lq <= LQ_MAX, FIRA_ERR_SHAPE, "attn_fwd: shape (Lq <= 32)");
-  FIRA_CHECK_ARG(!causal || Lq == Lk, FIRA_ERR_SHAPE, "attn_fwd: causal needs Lq == Lk");
+  FIRA_CHECK_ARG(!causal || (Lq == Lk && !ranges), FIRA_ERR_SHAPE, "attn_fwd: causal needs Lq == Lk and no ranges");
+  FIRA_CHECK_ARG(key_mask || ranges, FIRA_ERR_ARG, "attn_fwd: key_mask may only be NULL with ranges");
   FIRA_CHECK_ARG(dtype == FIRA_F32 || dtype == FIRA_BF16, FIRA_ERR_DTYPE, "attn_fwd: dtype %d", dtype);
   int rc;
   if ((rc = check_layout("attn_fwd", q, ldq, dtype)) || (rc = check_layout("attn_fwd", k, ldk, dtype)) ||
       (rc = check_layout("attn_fwd", v, ldv, dtype)))
     return rc;
-  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv))
-    return fira_attn_tc_fwd(q, ldq, k, ldk, v, ldv, key_mask, causal, ctx, ldo, stats, B, H, Lq, Lk, stream);
-  AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
+  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv, ranges != nullptr))
+    return fira_attn_tc_fwd(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, causal, ctx, ldo, stats, B, H, Lq, Lk, stream);
+  AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, ranges, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = fwd_smem(Lq, Lk);
   if (dtype == FIRA_F32) {
     if ((rc = set_smem(attn_fwd_kernel<float>, smem, "attn_fwd"))) return rc;
@@ -351,22 +361,24 @@ int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* 
   return FIRA_OK;
 }
 
-int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                  const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
-                  const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
-                  int Lq, int Lk, int d_head, int dtype, void* stream) {
+int attn_bwd_impl(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                  const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, const void* ctx,
+                  const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv,
+                  long lddv, int B, int H, int Lq, int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_bwd: d_head %d != 32", d_head);
   FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lq <= LQ_MAX, FIRA_ERR_SHAPE, "attn_bwd: shape (Lq <= 32)");
+  FIRA_CHECK_ARG(key_mask || ranges, FIRA_ERR_ARG, "attn_bwd: key_mask may only be NULL with ranges");
   FIRA_CHECK_ARG(dtype == FIRA_F32 || dtype == FIRA_BF16, FIRA_ERR_DTYPE, "attn_bwd: dtype %d", dtype);
   int rc;
   if ((rc = check_layout("attn_bwd", q, ldq, dtype)) || (rc = check_layout("attn_bwd", k, ldk, dtype)) ||
       (rc = check_layout("attn_bwd", v, ldv, dtype)) || (rc = check_layout("attn_bwd", ctx, ldo, dtype)) ||
       (rc = check_layout("attn_bwd", d_ctx, ldo, dtype)))
     return rc;
-  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv) && (lddk % 8) == 0 && (lddv % 8) == 0 && (lddq % 8) == 0)
-    return fira_attn_tc_bwd(q, ldq, k, ldk, v, ldv, key_mask, causal, ctx, d_ctx, ldo, stats, dq, lddq, dk, lddk, dv, lddv,
-                            B, H, Lq, Lk, stream);
-  AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
+  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv, ranges != nullptr) && (lddk % 8) == 0 && (lddv % 8) == 0 &&
+      (lddq % 8) == 0)
+    return fira_attn_tc_bwd(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, causal, ctx, d_ctx, ldo, stats, dq, lddq,
+                            dk, lddk, dv, lddv, B, H, Lq, Lk, stream);
+  AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, ranges, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = bwd_smem(Lq, Lk);
   if (dtype == FIRA_F32) {
     if ((rc = set_smem(attn_bwd_kernel<float>, smem, "attn_bwd"))) return rc;
@@ -380,6 +392,44 @@ int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* 
   }
   FIRA_CHECK_LAUNCH("fira_attn_bwd");
   return FIRA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                  const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
+                  int Lk, int d_head, int dtype, void* stream) {
+  FIRA_CHECK_ARG(key_mask, FIRA_ERR_ARG, "attn_fwd: null key_mask");
+  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, key_mask, nullptr, (long)B * Lk, causal, ctx, ldo, stats, B, H, Lq, Lk,
+                       d_head, dtype, stream);
+}
+
+int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
+                  const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
+                  const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
+                  int Lq, int Lk, int d_head, int dtype, void* stream) {
+  FIRA_CHECK_ARG(key_mask, FIRA_ERR_ARG, "attn_bwd: null key_mask");
+  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, key_mask, nullptr, (long)B * Lk, causal, ctx, d_ctx, ldo, stats, dq, lddq,
+                       dk, lddk, dv, lddv, B, H, Lq, Lk, d_head, dtype, stream);
+}
+
+int fira_attn_packed_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, void* ctx, long ldo, float* stats,
+                         int B, int H, int Lq, int d_head, int dtype, void* stream) {
+  FIRA_CHECK_ARG(ranges && kv_rows > 0, FIRA_ERR_ARG, "attn_packed_fwd: ranges / kv_rows");
+  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, 0, ctx, ldo, stats, B, H, Lq, mask_pitch, d_head,
+                       dtype, stream);
+}
+
+int fira_attn_packed_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, const void* ctx, const void* d_ctx,
+                         long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv,
+                         int B, int H, int Lq, int d_head, int dtype, void* stream) {
+  FIRA_CHECK_ARG(ranges && kv_rows > 0, FIRA_ERR_ARG, "attn_packed_bwd: ranges / kv_rows");
+  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, 0, ctx, d_ctx, ldo, stats, dq, lddq, dk, lddk,
+                       dv, lddv, B, H, Lq, mask_pitch, d_head, dtype, stream);
 }
 
 }  // extern "C"

@@ -36,7 +36,9 @@ constexpr int THREADS = 192;                         // warps 0-3: softmax / epi
 
 struct Args {
   const __nv_bfloat16* q; long ldq;
-  const unsigned char* key_mask;                     // [B, Lk]
+  const unsigned char* key_mask;                     // [B, Lk] (NULL with ranges: every key of the ranges is valid)
+  const int* ranges;                                 // NULL, or [B][4] = {first row, rows, first row, rows}: the keys of
+                                                     // commit b are two row ranges of k / v (packed batches); Lk = mask pitch
   int causal, B, H, Lq, Lk;
   float scale;
   __nv_bfloat16* ctx; long ldo;                      // fwd out / bwd: forward output
@@ -68,11 +70,26 @@ __device__ __forceinline__ void build_masked_tile(unsigned char* tile, const __n
   }
 }
 
-// score of key `key` for query t from the raw accumulator value
-__device__ __forceinline__ float masked_score(float raw, float scale, int key, int t, int Lk, int causal,
+// Key chunks of one commit: chunk c = rows [row[c], row[c] + n[c]) of k / v, its keys are mask positions moff[c] + i.
+struct Chunks { int nch; int row[MAX_CH]; int n[MAX_CH]; int moff[MAX_CH]; };
+
+__device__ __forceinline__ void make_chunks(Chunks& ch, const int* ranges, int b, int Lk) {
+  int n = 0;
+  if (ranges) {
+    const int s0 = ranges[4 * b], l0 = ranges[4 * b + 1], s1 = ranges[4 * b + 2], l1 = ranges[4 * b + 3];
+    for (int o = 0; o < l0 && n < MAX_CH; o += KC, ++n) { ch.row[n] = s0 + o; ch.n[n] = min(KC, l0 - o); ch.moff[n] = o; }
+    for (int o = 0; o < l1 && n < MAX_CH; o += KC, ++n) { ch.row[n] = s1 + o; ch.n[n] = min(KC, l1 - o); ch.moff[n] = l0 + o; }
+  } else {
+    for (int o = 0; o < Lk && n < MAX_CH; o += KC, ++n) { ch.row[n] = b * Lk + o; ch.n[n] = min(KC, Lk - o); ch.moff[n] = o; }
+  }
+  ch.nch = n;
+}
+
+// score of key i of a chunk for query t from the raw accumulator value (mpos = the key's mask position)
+__device__ __forceinline__ float masked_score(float raw, float scale, int i, int n_keys, int mpos, int t, int causal,
                                               const unsigned char* s_mask) {
-  if (key >= Lk) return -INFINITY;                   // tile overrun: not a key of this commit at all
-  const bool masked = s_mask[key] == 0 || (causal && key > t);
+  if (i >= n_keys) return -INFINITY;                 // tile overrun: not a key of this commit at all
+  const bool masked = s_mask[mpos] == 0 || (causal && mpos > t);
   return masked ? kMaskFill : raw * scale;
 }
 
@@ -84,12 +101,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __shared__ __align__(8) unsigned long long kv_full[MAX_CH], v_full[MAX_CH], s_full, p_full[2], p_empty[2], o_full;
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned char s_mask[MAX_CH * KC];
+  __shared__ Chunks ch;
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* sm = smem_raw + (base - smem_addr(smem_raw));
   constexpr uint32_t OFF_AQ = 0, OFF_KV = TILE, OFF_P = OFF_KV + MAX_CH * TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x >> 1, g = blockIdx.x & 1;
-  const int nch = (a.Lk + KC - 1) / KC;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_CH; ++i) { mbar_init(smem_addr(&kv_full[i]), 1); mbar_init(smem_addr(&v_full[i]), 1); }
@@ -99,19 +116,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     mbar_init_fence();
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    make_chunks(ch, a.ranges, b, a.Lk);
   }
   if (warp == 4) tmem_alloc(smem_addr(&tmem_slot), 512);
-  for (int i = threadIdx.x; i < MAX_CH * KC; i += THREADS) s_mask[i] = i < a.Lk ? a.key_mask[(long)b * a.Lk + i] : 0;
+  for (int i = threadIdx.x; i < MAX_CH * KC; i += THREADS)
+    s_mask[i] = i < a.Lk ? (a.key_mask ? a.key_mask[(long)b * a.Lk + i] : (unsigned char)1) : (unsigned char)0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const int nch = ch.nch;
   if (warp == 4 && lane == 0) {                      // K chunks can fly while the A' tile is built
     for (int c = 0; c < nch; ++c) {
       const uint32_t dst = base + OFF_KV + c * TILE, bar = smem_addr(&kv_full[c]);
       mbar_expect_tx(bar, TILE);
-      tma_load_2d(dst, &tmK, g * GF, b * a.Lk + c * KC, bar);
-      tma_load_2d(dst + PANEL, &tmK, g * GF + 64, b * a.Lk + c * KC, bar);
+      tma_load_2d(dst, &tmK, g * GF, ch.row[c], bar);
+      tma_load_2d(dst + PANEL, &tmK, g * GF + 64, ch.row[c], bar);
     }
   }
   build_masked_tile(sm + OFF_AQ, a.q, a.ldq, b, g, a.Lq, threadIdx.x, THREADS);
@@ -137,8 +157,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       for (int c = 0; c < nch; ++c) {
         const uint32_t dst = base + OFF_KV + c * TILE, bar = smem_addr(&v_full[c]);
         mbar_expect_tx(bar, TILE);
-        tma_load_2d(dst, &tmV, g * GF, b * a.Lk + c * KC, bar);
-        tma_load_2d(dst + PANEL, &tmV, g * GF + 64, b * a.Lk + c * KC, bar);
+        tma_load_2d(dst, &tmV, g * GF, ch.row[c], bar);
+        tma_load_2d(dst + PANEL, &tmV, g * GF + 64, ch.row[c], bar);
       }
       // ---- O' += P_c V_c : K-major A (P, 2 k-blocks of 64 keys), MN-major B (V: K = key rows, N = 128 features)
       constexpr uint32_t idesc_o = make_idesc_bf16(128, GF, false, true);
@@ -170,7 +190,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         tmem_ld32(trow + c * KC + j * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          mx = fmaxf(mx, masked_score(__uint_as_float(r[i]), a.scale, c * KC + j * 32 + i, t, a.Lk, a.causal, s_mask));
+          mx = fmaxf(mx, masked_score(__uint_as_float(r[i]), a.scale, j * 32 + i, ch.n[c], ch.moff[c] + j * 32 + i, t,
+                                      a.causal, s_mask));
       }
     float sum = 0.f;
     for (int c = 0; c < nch; ++c) {
@@ -184,7 +205,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         float e[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float s = masked_score(__uint_as_float(r[i]), a.scale, c * KC + j * 32 + i, t, a.Lk, a.causal, s_mask);
+          const float s = masked_score(__uint_as_float(r[i]), a.scale, j * 32 + i, ch.n[c], ch.moff[c] + j * 32 + i, t,
+                                       a.causal, s_mask);
           // the MMA consumes bf16(e): sum the ROUNDED values so that P rows are normalised exactly
           const float ev = live ? __bfloat162float(__float2bfloat16_rn(expf(s - mx))) : 0.f;
           e[i] = ev; sum += ev;
@@ -235,15 +257,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __shared__ __align__(8) unsigned long long kv_full, s_full, ds_full, g_full, epi_done;
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned char s_mask[MAX_CH * KC];
+  __shared__ Chunks ch;
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* sm = smem_raw + (base - smem_addr(smem_raw));
   constexpr uint32_t OFF_AQ = 0, OFF_ADO = TILE, OFF_K = 2 * TILE, OFF_V = 3 * TILE, OFF_P = 4 * TILE, OFF_DS = 5 * TILE;
   constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_DK = 384, T_DV = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x >> 1, g = blockIdx.x & 1;
-  const int nch = (a.Lk + KC - 1) / KC;
 
   if (threadIdx.x == 0) {
+    make_chunks(ch, a.ranges, b, a.Lk);
     mbar_init(smem_addr(&kv_full), 1);
     mbar_init(smem_addr(&s_full), 1);
     mbar_init(smem_addr(&ds_full), 128);
@@ -254,11 +277,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     tma_prefetch_desc(&tmV);
   }
   if (warp == 4) tmem_alloc(smem_addr(&tmem_slot), 512);
-  for (int i = threadIdx.x; i < MAX_CH * KC; i += THREADS) s_mask[i] = i < a.Lk ? a.key_mask[(long)b * a.Lk + i] : 0;
+  for (int i = threadIdx.x; i < MAX_CH * KC; i += THREADS)
+    s_mask[i] = i < a.Lk ? (a.key_mask ? a.key_mask[(long)b * a.Lk + i] : (unsigned char)1) : (unsigned char)0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const int nch = ch.nch;
   build_masked_tile(sm + OFF_AQ, a.q, a.ldq, b, g, a.Lq, threadIdx.x, THREADS);
   __syncthreads();
   build_masked_tile(sm + OFF_ADO, a.d_ctx, a.ldo, b, g, a.Lq, threadIdx.x, THREADS);
@@ -274,10 +299,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         if (c >= 1) mbar_wait(smem_addr(&epi_done), (c - 1) & 1);   // dK/dV of the previous chunk read out; K/V/P/dS free
         const uint32_t bar = smem_addr(&kv_full);
         mbar_expect_tx(bar, 2 * TILE);
-        tma_load_2d(base + OFF_K, &tmK, g * GF, b * a.Lk + c * KC, bar);
-        tma_load_2d(base + OFF_K + PANEL, &tmK, g * GF + 64, b * a.Lk + c * KC, bar);
-        tma_load_2d(base + OFF_V, &tmV, g * GF, b * a.Lk + c * KC, bar);
-        tma_load_2d(base + OFF_V + PANEL, &tmV, g * GF + 64, b * a.Lk + c * KC, bar);
+        tma_load_2d(base + OFF_K, &tmK, g * GF, ch.row[c], bar);
+        tma_load_2d(base + OFF_K + PANEL, &tmK, g * GF + 64, ch.row[c], bar);
+        tma_load_2d(base + OFF_V, &tmV, g * GF, ch.row[c], bar);
+        tma_load_2d(base + OFF_V + PANEL, &tmV, g * GF + 64, ch.row[c], bar);
         mbar_wait(bar, c & 1);
         tc_fence_after();
 #pragma unroll
@@ -338,9 +363,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         float pv[32], dsv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int key = c * KC + j * 32 + i;
-          const float s = masked_score(__uint_as_float(rs[i]), a.scale, key, t, a.Lk, a.causal, s_mask);
-          const bool masked = key >= a.Lk || s_mask[key] == 0 || (a.causal && key > t);
+          const int ki = j * 32 + i, mpos = ch.moff[c] + ki;
+          const float s = masked_score(__uint_as_float(rs[i]), a.scale, ki, ch.n[c], mpos, t, a.causal, s_mask);
+          const bool masked = ki >= ch.n[c] || s_mask[mpos] == 0 || (a.causal && mpos > t);
           const float p = live ? expf(s - mx) * inv : 0.f;                 // exp(-inf) = 0 beyond Lk
           pv[i] = p;
           dsv[i] = masked ? 0.f : p * (__uint_as_float(rp[i]) - delta) * a.scale;   // masked_fill blocks the gradient
@@ -367,15 +392,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       // ---- dK, dV rows of this chunk: thread = key row (warp*32 + lane), 128 features of the group
       mbar_wait(smem_addr(&g_full), c & 1);
       tc_fence_after();
-      const int key = c * KC + warp * 32 + lane;
+      const int ki = warp * 32 + lane;                 // key row of this chunk
 #pragma unroll 1
       for (int j = 0; j < GF / 32; ++j) {
         uint32_t rk[32], rv[32];
         tmem_ld32(trow + T_DK + j * 32, rk);
         tmem_ld32(trow + T_DV + j * 32, rv);
-        if (key < a.Lk) {
-          __nv_bfloat16* kd = a.dk + ((long)b * a.Lk + key) * a.lddk + g * GF + j * 32;
-          __nv_bfloat16* vd = a.dv + ((long)b * a.Lk + key) * a.lddv + g * GF + j * 32;
+        if (ki < ch.n[c]) {
+          __nv_bfloat16* kd = a.dk + (long)(ch.row[c] + ki) * a.lddk + g * GF + j * 32;
+          __nv_bfloat16* vd = a.dv + (long)(ch.row[c] + ki) * a.lddv + g * GF + j * 32;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float x[8], y[8];
@@ -408,23 +433,26 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-inline bool eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv) {
-  return d_head == DH && H == 2 * HG && Lq >= 1 && Lq <= 32 && Lk >= 1 && Lk <= MAX_CH * KC && (ldk % 8) == 0 && (ldv % 8) == 0;
+// with ranges (two row ranges per commit, Lk = mask pitch >= their total) every range starts its own chunk:
+// ceil(l0/128) + ceil(l1/128) <= 3 is guaranteed when l0 + l1 <= 256
+inline bool eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges) {
+  return d_head == DH && H == 2 * HG && Lq >= 1 && Lq <= 32 && Lk >= 1 && Lk <= (ranges ? 2 : MAX_CH) * KC &&
+         (ldk % 8) == 0 && (ldv % 8) == 0;
 }
 
 }  // namespace attn_tc
 
 // called by fira_attn_fwd / fira_attn_bwd (attention.cu) for the bf16 mode; returns FIRA_OK or an error code
 int fira_attn_tc_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                     const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
-                     int Lk, void* stream) {
+                     const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, void* ctx, long ldo,
+                     float* stats, int B, int H, int Lq, int Lk, void* stream) {
   using namespace attn_tc;
   CUtensorMap tk, tv;
-  int rc = tc::make_map_bf16(&tk, k, (long)B * Lk, 2 * GF, ldk, 64, KC, "attn_tc_fwd");
+  int rc = tc::make_map_bf16(&tk, k, kv_rows, 2 * GF, ldk, 64, KC, "attn_tc_fwd");
   if (rc) return rc;
-  if ((rc = tc::make_map_bf16(&tv, v, (long)B * Lk, 2 * GF, ldv, 64, KC, "attn_tc_fwd"))) return rc;
+  if ((rc = tc::make_map_bf16(&tv, v, kv_rows, 2 * GF, ldv, 64, KC, "attn_tc_fwd"))) return rc;
   Args a{};
-  a.q = (const __nv_bfloat16*)q; a.ldq = ldq; a.key_mask = key_mask; a.causal = causal; a.B = B; a.H = H; a.Lq = Lq;
+  a.q = (const __nv_bfloat16*)q; a.ldq = ldq; a.key_mask = key_mask; a.ranges = ranges; a.causal = causal; a.B = B; a.H = H; a.Lq = Lq;
   a.Lk = Lk; a.scale = 1.f / sqrtf((float)DH); a.ctx = (__nv_bfloat16*)ctx; a.ldo = ldo; a.stats = stats;
   const size_t smem = (1 + MAX_CH + 2) * (size_t)TILE + 1024;
   cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -435,16 +463,16 @@ int fira_attn_tc_fwd(const void* q, long ldq, const void* k, long ldk, const voi
 }
 
 int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                     const unsigned char* key_mask, int causal, const void* ctx, const void* d_ctx, long ldo,
-                     const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
-                     int Lq, int Lk, void* stream) {
+                     const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, const void* ctx,
+                     const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv,
+                     long lddv, int B, int H, int Lq, int Lk, void* stream) {
   using namespace attn_tc;
   CUtensorMap tk, tv;
-  int rc = tc::make_map_bf16(&tk, k, (long)B * Lk, 2 * GF, ldk, 64, KC, "attn_tc_bwd");
+  int rc = tc::make_map_bf16(&tk, k, kv_rows, 2 * GF, ldk, 64, KC, "attn_tc_bwd");
   if (rc) return rc;
-  if ((rc = tc::make_map_bf16(&tv, v, (long)B * Lk, 2 * GF, ldv, 64, KC, "attn_tc_bwd"))) return rc;
+  if ((rc = tc::make_map_bf16(&tv, v, kv_rows, 2 * GF, ldv, 64, KC, "attn_tc_bwd"))) return rc;
   Args a{};
-  a.q = (const __nv_bfloat16*)q; a.ldq = ldq; a.key_mask = key_mask; a.causal = causal; a.B = B; a.H = H; a.Lq = Lq;
+  a.q = (const __nv_bfloat16*)q; a.ldq = ldq; a.key_mask = key_mask; a.ranges = ranges; a.causal = causal; a.B = B; a.H = H; a.Lq = Lq;
   a.Lk = Lk; a.scale = 1.f / sqrtf((float)DH); a.ctx = (__nv_bfloat16*)const_cast<void*>(ctx); a.ldo = ldo;
   a.stats = const_cast<float*>(stats); a.d_ctx = (const __nv_bfloat16*)d_ctx;
   a.dq = (__nv_bfloat16*)dq; a.lddq = lddq; a.dk = (__nv_bfloat16*)dk; a.lddk = lddk; a.dv = (__nv_bfloat16*)dv; a.lddv = lddv;
@@ -456,6 +484,6 @@ int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const voi
   return FIRA_OK;
 }
 
-bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv) {
-  return attn_tc::eligible(B, H, Lq, Lk, d_head, ldk, ldv);
+bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges) {
+  return attn_tc::eligible(B, H, Lq, Lk, d_head, ldk, ldv, ranges);
 }

@@ -14,6 +14,16 @@ namespace {
 constexpr int D = 256;
 constexpr int TMAX = 32;   // tar_len 30 (run_model.py:32) padded
 
+// source row of (commit b, memory position s): padded batches b*S + s; packed batches (ranges[b] = {first code row,
+// code rows, first sub-token row, sub-token rows}) the s-th row of the two ranges, -1 beyond them
+__device__ __forceinline__ long src_row(const int* __restrict__ ranges, int b, int S, int s) {
+  if (!ranges) return (long)b * S + s;
+  const int* r = ranges + 4 * b;
+  if (s < r[1]) return r[0] + s;
+  s -= r[1];
+  return s < r[3] ? (long)(r[2] + s) : -1;
+}
+
 // ------------------------------------------------------------------ copy scores forward
 template <typename T>
 __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restrict__ src, const T* __restrict__ tgt,
@@ -21,6 +31,7 @@ __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restric
                                                               const float* __restrict__ b_res_p,
                                                               const unsigned char* __restrict__ src_mask,
                                                               const unsigned char* __restrict__ row_mask,
+                                                              const int* __restrict__ ranges,
                                                               float* __restrict__ sc, int B, int Tn, int S) {
   // src_mask / row_mask (optional): padded source positions are overwritten with -1e9 by the mixture kernel
   // (Model.py:61) and target rows without a label never reach the loss -- both are skipped (score 0 written).
@@ -37,12 +48,13 @@ __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restric
   const int rows_per_cta = 32;
   const int s_end = min(S, (int)(blockIdx.x + 1) * rows_per_cta);
   for (int s = blockIdx.x * rows_per_cta + warp; s < s_end; s += 8) {
-    if (src_mask && src_mask[(long)b * S + s] == 0) {
+    const long srow = src_row(ranges, b, S, s);
+    if (srow < 0 || (src_mask && src_mask[(long)b * S + s] == 0)) {
       for (int t = lane; t < Tn; t += 32) sc[((long)b * Tn + t) * S + s] = 0.f;
       continue;
     }
     float x[8];
-    Act<T>::load8(src + ((long)b * S + s) * D + lane * 8, x);
+    Act<T>::load8(src + srow * D + lane * 8, x);
     for (int t = 0; t < Tn; ++t) {
       if (row_mask && row_mask[(long)b * Tn + t] == 0) {          // warp-uniform
         if (lane == 0) sc[((long)b * Tn + t) * S + s] = 0.f;
@@ -66,6 +78,7 @@ __global__ void __launch_bounds__(256) copy_scores_bwd_kernel(const T* __restric
                                                               const float* __restrict__ w_res,
                                                               const float* __restrict__ d_sc,
                                                               const unsigned char* __restrict__ row_active,
+                                                              const int* __restrict__ ranges,
                                                               T* __restrict__ d_src, float* __restrict__ d_tgt,
                                                               float* __restrict__ d_w, float* __restrict__ d_b, int B,
                                                               int Tn, int S) {
@@ -98,10 +111,12 @@ __global__ void __launch_bounds__(256) copy_scores_bwd_kernel(const T* __restric
   const int rows_per_cta = 32;
   const int s_end = min(S, (int)(blockIdx.x + 1) * rows_per_cta);
   for (int s = blockIdx.x * rows_per_cta + warp; s < s_end; s += 8) {
+    const long srow = src_row(ranges, b, S, s);
+    if (srow < 0) continue;                            // beyond the commit's memory rows (packed batches)
     float x[8], dx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dx[i] = 0.f;
-    if (na > 0) Act<T>::load8(src + ((long)b * S + s) * D + lane * 8, x);
+    if (na > 0) Act<T>::load8(src + srow * D + lane * 8, x);
     for (int a = 0; a < na; ++a) {
       const int t = active_t[a];
       const float g = d_sc[((long)b * Tn + t) * S + s];
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(256) copy_scores_bwd_kernel(const T* __restric
       }
       dbias += g;
     }
-    Act<T>::store8(d_src + ((long)b * S + s) * D + lane * 8, dx);
+    Act<T>::store8(d_src + srow * D + lane * 8, dx);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red_w[warp][lane * 8 + i] = dw[i];
@@ -313,38 +328,66 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ log
 
 extern "C" {
 
-int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
-                         const unsigned char* src_mask, const unsigned char* row_mask, float* scores,
-                         int B, int T_len, int S, int dim, int dtype, void* stream) {
+static int copy_scores_fwd_impl(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
+                                const unsigned char* src_mask, const unsigned char* row_mask, const int* ranges,
+                                float* scores, int B, int T_len, int S, int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "copy_scores_fwd: dim %d != 256", dim);
   FIRA_CHECK_ARG(T_len > 0 && T_len <= TMAX, FIRA_ERR_SHAPE, "copy_scores_fwd: T_len %d > %d", T_len, TMAX);
   if (B == 0 || S == 0) return FIRA_OK;
   dim3 grid((S + 31) / 32, B);
   DISPATCH_T(dtype, copy_scores_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const T*)src_proj, (const T*)tgt_proj, w_res, b_res, src_mask, row_mask, scores, B, T_len, S);)
+      (const T*)src_proj, (const T*)tgt_proj, w_res, b_res, src_mask, row_mask, ranges, scores, B, T_len, S);)
   FIRA_CHECK_LAUNCH("fira_copy_scores_fwd");
   return FIRA_OK;
 }
 
-int fira_copy_scores_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
-                         const unsigned char* row_active, void* d_src_proj, float* d_tgt_proj, float* d_w_res,
-                         float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream) {
+static int copy_scores_bwd_impl(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
+                                const unsigned char* row_active, const int* ranges, void* d_src_proj, float* d_tgt_proj,
+                                float* d_w_res, float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "copy_scores_bwd: dim %d != 256", dim);
   FIRA_CHECK_ARG(T_len > 0 && T_len <= TMAX, FIRA_ERR_SHAPE, "copy_scores_bwd: T_len %d > %d", T_len, TMAX);
   if (B == 0 || S == 0) return FIRA_OK;
   dim3 grid((S + 31) / 32, B);
   const int smem = (int)sizeof(float) * (2 * TMAX * D + D + 8 * D);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(copy_scores_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(copy_scores_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
+  cudaError_t e = dtype == FIRA_F32
+      ? cudaFuncSetAttribute(copy_scores_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+      : cudaFuncSetAttribute(copy_scores_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "copy_scores_bwd attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   DISPATCH_T(dtype, copy_scores_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      (const T*)src_proj, (const T*)tgt_proj, w_res, d_scores, row_active, (T*)d_src_proj, d_tgt_proj, d_w_res,
+      (const T*)src_proj, (const T*)tgt_proj, w_res, d_scores, row_active, ranges, (T*)d_src_proj, d_tgt_proj, d_w_res,
       d_b_res, B, T_len, S);)
   FIRA_CHECK_LAUNCH("fira_copy_scores_bwd");
   return FIRA_OK;
+}
+
+int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
+                         const unsigned char* src_mask, const unsigned char* row_mask, float* scores,
+                         int B, int T_len, int S, int dim, int dtype, void* stream) {
+  return copy_scores_fwd_impl(src_proj, tgt_proj, w_res, b_res, src_mask, row_mask, nullptr, scores, B, T_len, S, dim,
+                              dtype, stream);
+}
+
+int fira_copy_scores_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
+                         const unsigned char* row_active, void* d_src_proj, float* d_tgt_proj, float* d_w_res,
+                         float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream) {
+  return copy_scores_bwd_impl(src_proj, tgt_proj, w_res, d_scores, row_active, nullptr, d_src_proj, d_tgt_proj, d_w_res,
+                              d_b_res, B, T_len, S, dim, dtype, stream);
+}
+
+int fira_copy_scores_packed_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
+                                const int* ranges, const unsigned char* src_mask, const unsigned char* row_mask,
+                                float* scores, int B, int T_len, int S, int dim, int dtype, void* stream) {
+  FIRA_CHECK_ARG(ranges, FIRA_ERR_ARG, "copy_scores_packed_fwd: null ranges");
+  return copy_scores_fwd_impl(src_proj, tgt_proj, w_res, b_res, src_mask, row_mask, ranges, scores, B, T_len, S, dim,
+                              dtype, stream);
+}
+
+int fira_copy_scores_packed_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
+                                const unsigned char* row_active, const int* ranges, void* d_src_proj, float* d_tgt_proj,
+                                float* d_w_res, float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream) {
+  FIRA_CHECK_ARG(ranges, FIRA_ERR_ARG, "copy_scores_packed_bwd: null ranges");
+  return copy_scores_bwd_impl(src_proj, tgt_proj, w_res, d_scores, row_active, ranges, d_src_proj, d_tgt_proj, d_w_res,
+                              d_b_res, B, T_len, S, dim, dtype, stream);
 }
 
 int fira_pointer_mix_nll_fwd(const void* logits, long ld_logits, const float* copy_scores, const float* gate_logits,

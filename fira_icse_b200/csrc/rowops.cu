@@ -27,14 +27,16 @@ __host__ inline int row_grid(long rows) {
 template <typename T>
 __global__ void embed_nodes_kernel(const int* __restrict__ sou, const int* __restrict__ sub, const int* __restrict__ ast,
                                    const float* __restrict__ emb, const float* __restrict__ ast_emb,
-                                   const float* __restrict__ pe, T* __restrict__ out_code, T* __restrict__ out_rest,
-                                   int B, int n_code, int n_sub, int n_ast) {
+                                   const float* __restrict__ pe, const int* __restrict__ pos_idx,
+                                   T* __restrict__ out_code, T* __restrict__ out_rest, int B, int n_code, int n_sub,
+                                   int n_ast) {
   const long R = (long)B * (n_code + n_sub + n_ast);
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < R; r += (long)gridDim.x * ROWS_PER_CTA) {
     const float* src; const float* pos = nullptr; T* dst;
     if (r < (long)B * n_code) {
-      src = emb + (long)sou[r] * D; pos = pe + (r % n_code) * D; dst = out_code + r * D;
+      // pos_idx (packed batches): position of the token inside its commit; padded batches: the column index
+      src = emb + (long)sou[r] * D; pos = pe + (long)(pos_idx ? pos_idx[r] : (int)(r % n_code)) * D; dst = out_code + r * D;
     } else if (r < (long)B * (n_code + n_sub)) {
       src = emb + (long)sub[r - (long)B * n_code] * D; dst = out_rest + r * D;
     } else {
@@ -354,6 +356,22 @@ __global__ void comb_gate3_bwd_kernel(const T* __restrict__ qp, const T* __restr
   }
 }
 
+// rows [off[0][B], Rc) and [Rc + off[1][B], Rc + Rs) of a packed batch's memory-row matrices are segment padding: no
+// kernel writes them, the GEMMs that follow read every row -> zero them (off = the packed batch's [3][B+1] row offsets).
+template <typename T>
+__global__ void zero_pad_rows_kernel(T* __restrict__ x, long ld, int width, const int* __restrict__ off, int B, int Rc,
+                                     int Rs) {
+  const int lo0 = off[B], lo1 = Rc + off[(B + 1) + B];
+  const long n0 = Rc - lo0, n1 = (long)Rc + Rs - lo1;
+  const int vec = width / 8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (n0 + n1) * vec; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / vec; const int c = (int)(i % vec);
+    const long row = r < n0 ? lo0 + r : lo1 + (r - n0);
+    float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Act<T>::store8(x + row * ld + c * 8, z);
+  }
+}
+
 // ------------------------------------------------------------------ column sums (bias gradients)
 // out[n] += sum_m x[m, n]; one warp covers 32 columns x a strided set of rows.
 template <typename T>
@@ -464,13 +482,28 @@ extern "C" {
 int fira_embed_nodes_fwd(const int* sou, const int* sub_token, const int* ast_change, const float* emb,
                          const float* ast_emb, const float* pos_table, void* out_code, void* out_rest, int B,
                          int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream) {
+  return fira_embed_nodes_pos_fwd(sou, nullptr, sub_token, ast_change, emb, ast_emb, pos_table, out_code, out_rest, B,
+                                  n_code, n_sub, n_ast, dim, dtype, stream);
+}
+
+int fira_embed_nodes_pos_fwd(const int* sou, const int* pos, const int* sub_token, const int* ast_change,
+                             const float* emb, const float* ast_emb, const float* pos_table, void* out_code,
+                             void* out_rest, int B, int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "embed_nodes: dim %d != 256", dim);
   FIRA_CHECK_ARG(fira_aligned16(out_code) && fira_aligned16(out_rest) && fira_aligned16(emb), FIRA_ERR_ALIGN,
                  "embed_nodes: 16-B alignment");
   const long R = (long)B * (n_code + n_sub + n_ast);
   DISPATCH_T(dtype, embed_nodes_kernel<T><<<row_grid(R), CTA, 0, (cudaStream_t)stream>>>(
-      sou, sub_token, ast_change, emb, ast_emb, pos_table, (T*)out_code, (T*)out_rest, B, n_code, n_sub, n_ast);)
+      sou, sub_token, ast_change, emb, ast_emb, pos_table, pos, (T*)out_code, (T*)out_rest, B, n_code, n_sub, n_ast);)
   FIRA_CHECK_LAUNCH("fira_embed_nodes_fwd");
+  return FIRA_OK;
+}
+
+int fira_zero_pad_rows(void* x, long ld, int width, const int* off, int B, int Rc, int Rs, int dtype, void* stream) {
+  FIRA_CHECK_ARG(x && off && B > 0 && width > 0 && width % 8 == 0 && ld >= width, FIRA_ERR_ARG, "zero_pad_rows: arguments");
+  FIRA_CHECK_ARG(fira_aligned16(x) && (ld % 8) == 0, FIRA_ERR_ALIGN, "zero_pad_rows: 16-B alignment");
+  DISPATCH_T(dtype, zero_pad_rows_kernel<T><<<148, 256, 0, (cudaStream_t)stream>>>((T*)x, ld, width, off, B, Rc, Rs);)
+  FIRA_CHECK_LAUNCH("fira_zero_pad_rows");
   return FIRA_OK;
 }
 

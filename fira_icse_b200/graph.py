@@ -67,6 +67,8 @@ class PackedEdges:
         """The same adjacency as a CSR in BUFFER order for the fused GCN layer kernel (fira_gcn_layer_fwd/bwd):
         rowptr indexed by the segment-major row of the node buffer, col = buffer rows.  -> (rowptr, col, val)."""
         key = (n_code, n_sub, n_ast)
+        if self.B == 1:                              # one graph: buffer order == node order, ids are already global
+            return self.rowptr, self.col, self.val
         if key not in self._rows:
             assert n_code + n_sub + n_ast == self.N
             R = self.B * self.N

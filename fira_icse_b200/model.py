@@ -85,6 +85,26 @@ class TransModel(nn.Module):
         pad = torch.zeros((tar_label.shape[0], 1), dtype=tar_label.dtype, device=tar_label.device)
         return torch.cat((tar_label[:, 1:], pad), dim=1)
 
+    def forward_packed(self, pb, stage="train"):
+        """The same computation on a per-commit PACKED batch (fira_icse_b200.packed.PackedBatch on this device, what
+        PackedBatchLoader(packed=True) emits): node rows = the real nodes of every commit, no 210/160/280 padding
+        (Dataset.py:80-94).  Loss, token count and gradients equal forward() on the padded batch; 'dev' ids number
+        copy positions by the commit's own memory rows (V + m, m < code rows + sub-token rows)."""
+        bf16 = self.precision == "bf16"
+        self.decoder.prefetch_weights()
+        pf_head = ops.prefetch_head(bf16, self.out_fc.weight, self.copy_net.LinearSource.weight,
+                                    self.copy_net.LinearTarget.weight)
+        memory = self.encoder.encode_memory_packed(pb)                       # [1, Rc + Rs, D]
+        dec = self.decoder(pb.tar, memory, pb.mem_mask, pb.tar_mask, packed=pb)
+        want_ids = stage != "train"
+        loss_sum, _, ids = ops.HeadFn.apply(want_ids, bf16, pf_head, memory, dec, pb.mem_mask, pb.label.view(-1),
+                                            self.out_fc.weight, self.out_fc.bias, *self.copy_net.flat_params(), pb)
+        if stage == "train":
+            return loss_sum, (pb.label != 0).sum()
+        elif stage == "dev" or stage == "test":
+            return ids.long()
+        raise ValueError(f"unknown stage {stage!r}")
+
     def forward(self, sou, tar, attr, mark, ast_change, edge, tar_label, sub_token, stage="train"):
         dev = self.out_fc.weight.device
         sou, tar, mark, ast_change, tar_label, sub_token = (

@@ -199,6 +199,21 @@ class Encoder(nn.Module):
                                    self._pos(dev), self.embedding.weight, self.ast_change_embedding.weight,
                                    self.mark_embedding.weight, *lp)
 
+    def encode_memory_packed(self, pb):
+        """Packed batch (fira_icse_b200.packed.PackedBatch on this device) -> memory rows [1, Rc + Rs, D]: the code rows
+        then the sub-token rows of every commit (commit b owns the two row ranges pb.ranges[b]).  The batch runs as ONE
+        ragged graph through the same kernels (B = 1, segments = the three row blocks, global adjacency)."""
+        dev = self.embedding.weight.device
+        cfg = _run_cfg(self)
+        cfg.update(p_comb=self.combination_list2[0].dropout.p, p_gcn=self.gcn_list[0].dropout.p, pos=pb.pos)
+        lp = []
+        for comb, gcn in zip(self.combination_list2, self.gcn_list):
+            lp += comb.flat_params() + gcn.flat_params()
+        edges = PackedEdges(pb.rowptr, pb.col, pb.val, 1, pb.rows, True)
+        return ops.EncoderFn.apply(cfg, pb.code.view(1, -1), pb.mark.view(1, -1), pb.ast.view(1, -1), pb.sub.view(1, -1),
+                                   edges, self._pos(dev), self.embedding.weight, self.ast_change_embedding.weight,
+                                   self.mark_embedding.weight, *lp)
+
     def forward(self, input_token, sou_mask, attr, mark, ast_change, edge, sub_token):
         # `attr` and `sou_mask` are accepted and unused, exactly like gnn_transformer.py:45
         memory = self.encode_memory(input_token, mark, ast_change, edge, sub_token)
@@ -236,12 +251,14 @@ class Decoder(nn.Module):
         if dev.type == "cuda":
             self._prefetched = ops.prefetch_decoder(bool(getattr(self, "bf16", False)), self._flat(), dev)
 
-    def forward(self, output_token, input_em, sou_mask, tar_mask_pad):
+    def forward(self, output_token, input_em, sou_mask, tar_mask_pad, packed=None):
+        """packed: a packed.PackedBatch -- `input_em` is then the [1, Rc + Rs, D] memory-row matrix of
+        Encoder.encode_memory_packed and `sou_mask` the [B, S] mask over each commit's own memory rows"""
         dev = self.embedding.weight.device
         if self.pos_encode.device != dev:
             self.pos_encode = self.pos_encode.to(dev)
         cfg = _run_cfg(self)
-        cfg.update(p_dec=self.attention_list[0].dropout.p, prefetch=getattr(self, "_prefetched", None))
+        cfg.update(p_dec=self.attention_list[0].dropout.p, prefetch=getattr(self, "_prefetched", None), packed=packed)
         self._prefetched = None
         lp = self._flat()
         return ops.DecoderFn.apply(cfg, _i32(output_token), input_em, _u8(sou_mask), _u8(tar_mask_pad),

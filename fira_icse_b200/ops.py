@@ -343,8 +343,14 @@ class EncoderFn(torch.autograd.Function):
 
         Xc = pr.empty((Mc, D), dev)
         Gin = pr.empty((R, D), dev)
-        call("fira_embed_nodes_fwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(emb), _ptr(ast_emb),
-             _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
+        # packed batches (packed.py) come as ONE ragged "graph": B = 1, the three segments hold the real rows of every
+        # commit, cfg["pos"] gives each code row its position inside its commit (positional encoding)
+        if cfg.get("pos") is not None:
+            call("fira_embed_nodes_pos_fwd", _ptr(sou), _ptr(cfg["pos"]), _ptr(sub_token), _ptr(ast_change), _ptr(emb),
+                 _ptr(ast_emb), _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
+        else:
+            call("fira_embed_nodes_fwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(emb), _ptr(ast_emb),
+                 _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
         # bf16 mode: the GCN layer is ONE fused kernel (gather -> tcgen05 -> LayerNorm epilogue, csrc/gcn_fused.cu);
         # FIRA_GCN_FUSED=0 keeps the three-launch sequence (scatter, GEMM, LayerNorm) for A/B measurements
         fused = pr.bf16 and os.environ.get("FIRA_GCN_FUSED", "0") != "0"      # TODO default on once validated on the GPU
@@ -499,8 +505,9 @@ class DecoderFn(torch.autograd.Function):
     def forward(ctx, cfg, tar, memory, mem_mask, tar_mask, pos_table, dec_emb, *lp):
         _require_cuda(tar, memory, dec_emb)
         B, T = tar.shape
-        S = memory.shape[1]
-        Mt, Ms = B * T, B * S
+        pk = cfg.get("packed")                      # packed batch: memory is [1, Rc + Rs, D], keys of commit b = pk.ranges[b]
+        S = pk.S if pk is not None else memory.shape[1]
+        Mt, Ms = B * T, memory.shape[0] * memory.shape[1]
         L = len(lp) // DEC_LAYER_PARAMS
         H = cfg["heads"]
         training, seed = cfg["training"], cfg["seed"]
@@ -543,8 +550,12 @@ class DecoderFn(torch.autograd.Function):
             Q = pr.linear(X1, cWq, cbq)
             ctx2 = pr.empty((Mt, D), dev)
             st2 = torch.empty((B, H, T, 2), **f32)
-            call("fira_attn_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
-                 _ptr(mem_mask), 0, _ptr(ctx2), D, _ptr(st2), B, H, T, S, D // H, pr.code, st)
+            if pk is not None:
+                call("fira_attn_packed_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
+                     _ptr(pk.ranges), Ms, _ptr(mem_mask), S, _ptr(ctx2), D, _ptr(st2), B, H, T, D // H, pr.code, st)
+            else:
+                call("fira_attn_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
+                     _ptr(mem_mask), 0, _ptr(ctx2), D, _ptr(st2), B, H, T, S, D // H, pr.code, st)
             Z2 = pr.linear(ctx2, cWo, cbo)
             X2 = pr.empty((Mt, D), dev)
             ls2 = pr.ln_fwd(Z2, X1, clw, clb, X2, X2, Mt, Mt, p, seed, sid + 1)
@@ -557,15 +568,16 @@ class DecoderFn(torch.autograd.Function):
             X = X3
         ctx.saved = saved
         ctx.wcache = pr.wcache
-        ctx.misc = (cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p, mem_dtype)
+        ctx.misc = (cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p, mem_dtype, Ms)
         ctx.save_for_backward(dec_emb, *lp)
         return X.view(B, T, D)
 
     @staticmethod
     def backward(ctx, d_out):
-        cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p, mem_dtype = ctx.misc
+        cfg, tar, memory, mem_mask, tar_mask, KV, Wkv, B, T, S, p, mem_dtype, Ms = ctx.misc
         dec_emb, *lp = ctx.saved_tensors
-        Mt, Ms = B * T, B * S
+        Mt = B * T
+        pk = cfg.get("packed")
         L = len(lp) // DEC_LAYER_PARAMS
         H, seed = cfg["heads"], cfg["seed"]
         pr = Prec(cfg.get("bf16", False), ctx.wcache, seed_ctr=cfg.get("seed_ctr"))
@@ -574,6 +586,8 @@ class DecoderFn(torch.autograd.Function):
         ldkv = L * 2 * D
         dX = d_out.contiguous().to(pr.tdt).view(Mt, D)
         dKV = pr.empty((Ms, ldkv), dev)
+        if pk is not None:          # the attention kernels write the rows of every commit; the segment padding stays
+            call("fira_zero_pad_rows", _ptr(dKV), ldkv, ldkv, _ptr(pk.off), B, pk.Rc, pk.Rs, pr.code, st)
         grads = [None] * len(lp)
         F = 4 * D
         fork = Fork(dev)
@@ -601,9 +615,14 @@ class DecoderFn(torch.autograd.Function):
                 d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D)
             dctx2 = pr.linear_dx(dZ2, D, cWo, Mt)
             dQ = pr.empty((Mt, D), dev)
-            call("fira_attn_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
-                 _ptr(mem_mask), 0, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
-                 _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
+            if pk is not None:
+                call("fira_attn_packed_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
+                     _ptr(pk.ranges), Ms, _ptr(mem_mask), S, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D,
+                     _ptr(dKV, i * 2 * D), ldkv, _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, D // H, pr.code, st)
+            else:
+                call("fira_attn_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
+                     _ptr(mem_mask), 0, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
+                     _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
             with fork(dQ, X1):
                 d_cbq = colsum(dQ, D, Mt, D)
                 d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D)
@@ -634,7 +653,7 @@ class DecoderFn(torch.autograd.Function):
         with fork(dKV, mem2):
             d_bkv = colsum(dKV, ldkv, Ms, ldkv)
             d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D)
-        d_mem = pr.linear_dx(dKV, ldkv, Wkv, Ms).view(B, S, D).to(mem_dtype)
+        d_mem = pr.linear_dx(dKV, ldkv, Wkv, Ms).view(memory.shape).to(mem_dtype)
         for i in range(L):
             o = i * 2 * D
             grads[i * 26 + 12], grads[i * 26 + 13] = d_Wkv[o:o + D], d_bkv[o:o + D]
@@ -650,12 +669,16 @@ def _ld_logits(V):
     return (V + 63) // 64 * 64
 
 
-def copy_scores_fwd(pr, memory2, dec2, Ws, Wt, wres, bres, B, T, S, src_mask=None, row_mask=None):
-    src = pr.linear(memory2, Ws)                  # [B*S, 256]
+def copy_scores_fwd(pr, memory2, dec2, Ws, Wt, wres, bres, B, T, S, src_mask=None, row_mask=None, ranges=None):
+    src = pr.linear(memory2, Ws)                  # [B*S, 256] (packed batches: [Rc + Rs, 256])
     tgt = pr.linear(dec2, Wt)                     # [B*T, 256]
     sc = torch.empty((B, T, S), dtype=torch.float32, device=dec2.device)
-    call("fira_copy_scores_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(src_mask), _ptr(row_mask),
-         _ptr(sc), B, T, S, D, pr.code, _stream())
+    if ranges is not None:
+        call("fira_copy_scores_packed_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(ranges), _ptr(src_mask),
+             _ptr(row_mask), _ptr(sc), B, T, S, D, pr.code, _stream())
+    else:
+        call("fira_copy_scores_fwd", _ptr(src), _ptr(tgt), _ptr(wres), _ptr(bres), _ptr(src_mask), _ptr(row_mask),
+             _ptr(sc), B, T, S, D, pr.code, _stream())
     return src, tgt, sc
 
 
@@ -665,12 +688,13 @@ class HeadFn(torch.autograd.Function):
     is never built."""
 
     @staticmethod
-    def forward(ctx, want_argmax, bf16, pf, memory, dec, mem_mask, label, Wout, bout, Ws, Wt, Wres, bres, Wp, bp):
+    def forward(ctx, want_argmax, bf16, pf, memory, dec, mem_mask, label, Wout, bout, Ws, Wt, Wres, bres, Wp, bp,
+                pk=None):
         _require_cuda(memory, dec, Wout)
-        B, S, _ = memory.shape
-        T = dec.shape[1]
+        B, T = dec.shape[0], dec.shape[1]
+        S = pk.S if pk is not None else memory.shape[1]      # packed batch: memory is [1, Rc + Rs, D]
         V = Wout.shape[0]
-        Mt, Ms = B * T, B * S
+        Mt, Ms = B * T, memory.shape[0] * memory.shape[1]
         pr = Prec(bf16)
         if pf is not None and pf.event is not None:
             torch.cuda.current_stream().wait_event(pf.event)
@@ -689,7 +713,7 @@ class HeadFn(torch.autograd.Function):
         # label (vocabulary-label rows take their loss from the vocabulary softmax alone, Model.py:64-81)
         row_mask = None if want_argmax else (label >= V).to(torch.uint8)
         src, tgt, sc = copy_scores_fwd(pr, memory2, dec2, Ws, Wt, Wres, bres, B, T, S, src_mask=mem_mask,
-                                       row_mask=row_mask)
+                                       row_mask=row_mask, ranges=pk.ranges if pk is not None else None)
         gl = linear(dec32, Wp, bp)                # fp32 [Mt, 2]
         stats = torch.empty((Mt, 8), **f32)
         nll = torch.empty((Mt,), **f32)
@@ -697,7 +721,7 @@ class HeadFn(torch.autograd.Function):
         call("fira_pointer_mix_nll_fwd", _ptr(logits), ldl, _ptr(sc), _ptr(gl), _ptr(mem_mask), _ptr(label),
              _ptr(stats), _ptr(nll), _ptr(amax), Mt, T, V, S, pr.code, st)
         ctx.misc = (pr, memory2, dec2, dec32, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V,
-                    memory.dtype, dec.dtype)
+                    memory.dtype, dec.dtype, pk, memory.shape)
         ctx.save_for_backward(Wout, Ws, Wt, Wres, Wp)
         loss_sum = colsum(nll, 1, Mt, 1).view(())
         ids = amax.view(B, T) if want_argmax else None
@@ -708,9 +732,9 @@ class HeadFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_nll, g_ids):
         (pr, memory2, dec2, dec32, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V,
-         mem_dt, dec_dt) = ctx.misc
+         mem_dt, dec_dt, pk, mem_shape) = ctx.misc
         Wout, Ws, Wt, Wres, Wp = ctx.saved_tensors
-        Mt, Ms = B * T, B * S
+        Mt, Ms = B * T, memory2.shape[0]
         dev = dec2.device
         f32 = dict(dtype=torch.float32, device=dev)
         st = _stream()
@@ -726,8 +750,13 @@ class HeadFn(torch.autograd.Function):
         d_tgt = torch.zeros((Mt, D), **f32)
         d_wres = torch.zeros((1, D), **f32)
         d_bres = torch.zeros((1,), **f32)
-        call("fira_copy_scores_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(d_src),
-             _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
+        if pk is not None:
+            call("fira_zero_pad_rows", _ptr(d_src), D, D, _ptr(pk.off), B, pk.Rc, pk.Rs, pr.code, st)
+            call("fira_copy_scores_packed_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(pk.ranges),
+                 _ptr(d_src), _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
+        else:
+            call("fira_copy_scores_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(d_src),
+                 _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
         fork = Fork(dev)
         with fork(d_src, memory2, dlogits, dec2, dgl, dec32, d_tgt):
             d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D)
@@ -747,8 +776,8 @@ class HeadFn(torch.autograd.Function):
         linear_dx(dgl, 2, Wp, Mt, out=d_dec, accumulate=True)
         linear_dx(d_tgt, D, Wt, Mt, out=d_dec, accumulate=True)
         fork.join()
-        return (None, None, None, d_mem.view(B, S, D).to(mem_dt), d_dec.view(B, T, D).to(dec_dt), None, None, d_Wout, d_bout,
-                d_Ws, d_Wt, d_wres, d_bres, d_Wp, d_bp)
+        return (None, None, None, d_mem.view(mem_shape).to(mem_dt), d_dec.view(B, T, D).to(dec_dt), None, None, d_Wout,
+                d_bout, d_Ws, d_Wt, d_wres, d_bres, d_Wp, d_bp, None)
 
 
 # ============================================================================= module-surface pieces

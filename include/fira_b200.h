@@ -66,6 +66,13 @@ int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long
 int fira_embed_nodes_fwd(const int* sou, const int* sub_token, const int* ast_change, const float* emb,
                          const float* ast_emb, const float* pos_table, void* out_code, void* out_rest, int B,
                          int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream);
+/* The same with an explicit position per code row (packed batches, fira_icse_b200/packed.py: `pos` = index of the token
+ * inside its commit; B = 1, n_code / n_sub / n_ast = the padded row counts of the three segments). */
+int fira_embed_nodes_pos_fwd(const int* sou, const int* pos, const int* sub_token, const int* ast_change,
+                             const float* emb, const float* ast_emb, const float* pos_table, void* out_code,
+                             void* out_rest, int B, int n_code, int n_sub, int n_ast, int dim, int dtype, void* stream);
+/* Zero the segment-padding rows of a packed batch's [Rc + Rs, ld] memory-row matrix (off = its [3][B+1] row offsets). */
+int fira_zero_pad_rows(void* x, long ld, int width, const int* off, int B, int Rc, int Rs, int dtype, void* stream);
 int fira_embed_nodes_bwd(const int* sou, const int* sub_token, const int* ast_change, const void* d_code,
                          const void* d_rest, float* d_emb, float* d_ast_emb, int B, int n_code, int n_sub, int n_ast,
                          int dim, int dtype, void* stream);
@@ -154,6 +161,18 @@ int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* 
                   const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
                   int Lq, int Lk, int d_head, int dtype, void* stream);
 
+/* Cross-attention of a PACKED batch (fira_icse_b200/packed.py): the keys / values of commit b are two row ranges of
+ * k / v, ranges[b] = {first row, rows, first row, rows} (code rows, sub-token rows; GLOBAL row ids, kv_rows = rows of
+ * k / v), key_mask [B, mask_pitch] over the commit's own key positions (NULL: all valid), mask_pitch >= rows of any
+ * commit.  Rows of dk / dv outside every range are not written (fira_zero_pad_rows clears the segment padding). */
+int fira_attn_packed_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, void* ctx, long ldo, float* stats,
+                         int B, int H, int Lq, int d_head, int dtype, void* stream);
+int fira_attn_packed_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, const void* ctx, const void* d_ctx,
+                         long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv,
+                         int B, int H, int Lq, int d_head, int dtype, void* stream);
+
 /* ---- CopyNet scores (Model.py:17-18): sc[b,t,s] = b_res + w_res . tanh(src[b,s] + tgt[b,t]).
  *      src_mask [B,S] / row_mask [B*T] (optional, 1 = compute): positions the caller will mask anyway. */
 int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
@@ -162,6 +181,16 @@ int fira_copy_scores_fwd(const void* src_proj, const void* tgt_proj, const float
 int fira_copy_scores_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
                          const unsigned char* row_active, void* d_src_proj, float* d_tgt_proj, float* d_w_res,
                          float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream);
+
+/* The same for a PACKED batch: the source rows of commit b are the two row ranges ranges[b] of src_proj (global rows);
+ * scores stay [B, T, S] over the commit's own memory positions (S = mask pitch); d_src_proj rows outside the ranges
+ * are not written. */
+int fira_copy_scores_packed_fwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* b_res,
+                                const int* ranges, const unsigned char* src_mask, const unsigned char* row_mask,
+                                float* scores, int B, int T_len, int S, int dim, int dtype, void* stream);
+int fira_copy_scores_packed_bwd(const void* src_proj, const void* tgt_proj, const float* w_res, const float* d_scores,
+                                const unsigned char* row_active, const int* ranges, void* d_src_proj, float* d_tgt_proj,
+                                float* d_w_res, float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream);
 
 /* ---- dual-copy mixture, loss and argmax (Model.py:54-86).  stats: 8 floats per row
  *      (vmax, vsum, cmax, csum, g0, g1, p_label, 0).  argmax_out may be NULL (training). */
