@@ -321,11 +321,24 @@ def run_gpu_arm(args):
     model.set_precision(args.precision)
 
     # every rank gets its own shard of the synthetic stream (graphs shard by commit, no data collective)
-    pool_host = [host_batch((rank * N_POOL + i) * B, B, pin=True, trim=args.trim) for i in range(N_POOL)]
-    full_host = pool_host[0] if not args.trim else host_batch(rank * N_POOL * B, B, pin=True, trim=False)
-    pool_dev = [device_batch(hb, dev, B) for hb in pool_host]
+    packed = args.layout == "packed"
+    full_host = host_batch(rank * N_POOL * B, B, pin=True, trim=False)
+    if packed:
+        # per-commit packed batches (fira_icse_b200/packed.py): node rows = the real nodes of every commit
+        from fira_icse_b200.packed import PackedTables, pack_from_dataset
+        from fira_icse_b200.synth import SynthDataset
+        synth_ds = SynthDataset(rank * N_POOL * B, N_POOL * B, VOCAB, AST_VOCAB)
+        synth_tables = PackedTables(synth_ds)
+        import numpy as np
+        pool_host = [pack_from_dataset(synth_tables, np.arange(i * B, (i + 1) * B), VOCAB, pin=True) for i in range(N_POOL)]
+        pool_dev = [pb.to(dev) for pb in pool_host]
+    else:
+        pool_host = [host_batch((rank * N_POOL + i) * B, B, pin=True, trim=args.trim) for i in range(N_POOL)]
+        pool_dev = [device_batch(hb, dev, B) for hb in pool_host]
 
     def host_list(hb):
+        if packed:
+            return hb
         t, csr, _ = hb
         return [t["sou"], t["tar"], None, t["mark"], t["ast_change"], csr, t["tar_label"], t["sub_token"]]
     torch.cuda.synchronize()
@@ -351,7 +364,8 @@ def run_gpu_arm(args):
     last_loss = [0.0]
     if args.graph:
         # whole step captured in a CUDA graph (fira_icse_b200/engine.py): one cudaGraphLaunch per step
-        eng = GraphedTrainStep(model, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True))
+        eng = GraphedTrainStep(model, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True),
+                               edge_capacity=(max(pb.nnz for pb in pool_host) + 4095) // 4096 * 4096 * 2 if packed else None)
         eng.load(pool_dev[0])
         eng.capture()                                                # one eager step + capture of this shape
         for hb in pool_dev[1:]:                                      # trimmed batches come in a few shapes:
@@ -369,6 +383,8 @@ def run_gpu_arm(args):
             eng.step(host_list(pool_host[i % N_POOL]))               # pinned host -> static device buffers -> replay
             last_loss[0] = (eng.loss_sum / eng.n_local).item()       # D2H read of the step's result
     else:
+        if packed:
+            raise SystemExit("bench.py: --layout packed runs through the graph engine (drop --no-graph)")
         dp = DataParallelStep(model, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True))
         optimizer, bucket = dp.optimizer, dp.bucket
         launches_per_step = None
@@ -401,13 +417,13 @@ def run_gpu_arm(args):
     # ---- the same, fed by the native loader: packed split arrays -> C++ gather/trim/CSR pack into pinned staging
     #      buffers on a background thread (data.PackedBatchLoader) -> H2D -> graph replay -> loss D2H
     loader_info = None
-    if args.graph and args.trim:
+    if args.graph and (args.trim or packed):
         from fira_icse_b200.data import PackedBatchLoader
         from fira_icse_b200.synth import SynthDataset
         ds = SynthDataset(rank * N_POOL * B, N_POOL * B, VOCAB, AST_VOCAB)      # the commits of pool_host, in order
         import numpy as np
         laps = (args.steps + N_POOL) // N_POOL + 2                   # one long epoch cycling through the same batches
-        ld = PackedBatchLoader(ds, B, VOCAB, shuffle=False, multiples=(8, 8, 8), prefetch=2,
+        ld = PackedBatchLoader(ds, B, VOCAB, shuffle=False, multiples=(8, 8, 8), prefetch=2, packed=packed,
                                indices=np.tile(np.arange(N_POOL * B), laps))
         stream_of_batches = iter(ld)
 
@@ -419,7 +435,8 @@ def run_gpu_arm(args):
         ms_ld = timed(loader_step, args.steps)
         loader_info = {"value": world * B * args.steps / (ms_ld * 1e-3), "unit": "commits/s",
                        "ms_per_step": ms_ld / args.steps,
-                       "api": "PackedBatchLoader (fira_host_gather_batch, pinned staging ring) -> GraphedTrainStep.step"}
+                       "api": ("PackedBatchLoader(packed=True) (fira_host_gather_packed" if packed else
+                               "PackedBatchLoader (fira_host_gather_batch") + ", pinned staging ring) -> GraphedTrainStep.step"}
 
     # ---- the reference-facing call with the reference's own input format: dense fp64 adjacency on the host
     dense_info = None
@@ -476,15 +493,21 @@ def run_gpu_arm(args):
                                           "fp32 parity (fp32 storage, fp32 FFMA accumulate)"),
                        "optimizer": "Adam lr 1e-4 (torch fused), dropout on (0.1 / GCN 0.2)",
                        "launch": "whole step replayed as one CUDA graph" if args.graph else "eager launches",
-                       "padding": ("loader trims the padding the batch shares (code/sub-token/AST segments cut to the "
+                       "padding": ("per-commit packed batches: node rows = the real nodes of every commit (segments padded to "
+                                   "1024/512/512-row buckets); loss and gradients equal the padded batch" if packed else
+                                   "loader trims the padding the batch shares (code/sub-token/AST segments cut to the "
                                    "batch maximum, multiple of 8); real rows, loss and gradients unchanged"
                                    if args.trim else "full 210/160/280 padding"),
-                       "batch_shapes": sorted({(hb[0]["sou"].shape[1], hb[0]["sub_token"].shape[1],
-                                                hb[0]["ast_change"].shape[1]) for hb in pool_host}),
+                       "batch_shapes": (sorted({pb.shape_key for pb in pool_host}) if packed else
+                                        sorted({(hb[0]["sou"].shape[1], hb[0]["sub_token"].shape[1],
+                                                 hb[0]["ast_change"].shape[1]) for hb in pool_host})),
                        "l2": f"{N_POOL} distinct batches rotated; one step touches >1 GB of activations (> 126 MB L2)"},
-            "e2e": {"value": e2e_value, "unit": "commits/s", "h2d_bytes_per_step": int(h2d_bytes(pool_host[0])),
+            "e2e": {"value": e2e_value, "unit": "commits/s",
+                    "h2d_bytes_per_step": int(pool_host[0].h2d_bytes() if packed else h2d_bytes(pool_host[0])),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                    "api": "TransModel.forward(sou,tar,attr,mark,ast_change,PackedEdges,tar_label,sub_token,'train')"},
+                    "api": ("GraphedTrainStep.step(pinned host batch): H2D into the static buffers -> replay of the captured "
+                            "TransModel." + ("forward_packed" if packed else "forward") + " + backward + Adam graph -> loss D2H"
+                            if args.graph else "DataParallelStep.step: TransModel.forward eager + backward + Adam")},
             "e2e_loader": loader_info,
             "e2e_dense_edge": dense_info,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_scatter_fp32": roof_f32,
@@ -503,6 +526,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FIRA_PRECISION", "bf16"), choices=["bf16", "fp32"],
                     help="bf16 = BASELINE.json config (default); fp32 = parity mode")
+    ap.add_argument("--layout", default=os.environ.get("FIRA_LAYOUT", "trimmed"), choices=["trimmed", "packed"],
+                    help="trimmed = padded batches cut to the batch maximum; packed = per-commit packed node rows")
     ap.add_argument("--no-trim", dest="trim", action="store_false",
                     help="feed fully padded 210/160/280 batches instead of loader-trimmed ones")
     ap.add_argument("--no-graph", dest="graph", action="store_false",

@@ -23,13 +23,13 @@ int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const voi
                      const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, const void* ctx,
                      const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv,
                      long lddv, int B, int H, int Lq, int Lk, void* stream);
-bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges);
+bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, int max_chunks);
 
 namespace {
 
 // bf16 activations go to the tensor-core kernels unless FIRA_ATTN_TC=0 (A/B runs against the FFMA kernels below)
-bool use_tc(int dtype, int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges = false) {
-  if (dtype != FIRA_BF16 || !fira_attn_tc_eligible(B, H, Lq, Lk, d_head, ldk, ldv, ranges)) return false;
+bool use_tc(int dtype, int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, int max_chunks) {
+  if (dtype != FIRA_BF16 || !fira_attn_tc_eligible(B, H, Lq, Lk, d_head, ldk, ldv, max_chunks)) return false;
   const char* e = getenv("FIRA_ATTN_TC");
   return e ? atoi(e) != 0 : false;      // TODO default on once validated on the GPU
 }
@@ -335,8 +335,8 @@ int check_layout(const char* name, const void* p, long ld, int dtype) {
 namespace {
 
 int attn_fwd_impl(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                  const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, void* ctx, long ldo,
-                  float* stats, int B, int H, int Lq, int Lk, int d_head, int dtype, void* stream) {
+                  const unsigned char* key_mask, const int* ranges, long kv_rows, int max_chunks, int causal, void* ctx,
+                  long ldo, float* stats, int B, int H, int Lq, int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_fwd: d_head %d != 32", d_head);
   FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lq <= LQ_MAX, FIRA_ERR_SHAPE, "attn_fwd: shape (Lq <= 32)");
   FIRA_CHECK_ARG(!causal || (Lq == Lk && !ranges), FIRA_ERR_SHAPE, "attn_fwd: causal needs Lq == Lk and no ranges");
@@ -346,7 +346,7 @@ int attn_fwd_impl(const void* q, long ldq, const void* k, long ldk, const void* 
   if ((rc = check_layout("attn_fwd", q, ldq, dtype)) || (rc = check_layout("attn_fwd", k, ldk, dtype)) ||
       (rc = check_layout("attn_fwd", v, ldv, dtype)))
     return rc;
-  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv, ranges != nullptr))
+  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv, max_chunks))
     return fira_attn_tc_fwd(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, causal, ctx, ldo, stats, B, H, Lq, Lk, stream);
   AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, ranges, causal, B, H, Lq, Lk, 1.f / sqrtf((float)d_head)};
   const size_t smem = fwd_smem(Lq, Lk);
@@ -362,9 +362,9 @@ int attn_fwd_impl(const void* q, long ldq, const void* k, long ldk, const void* 
 }
 
 int attn_bwd_impl(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
-                  const unsigned char* key_mask, const int* ranges, long kv_rows, int causal, const void* ctx,
-                  const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv,
-                  long lddv, int B, int H, int Lq, int Lk, int d_head, int dtype, void* stream) {
+                  const unsigned char* key_mask, const int* ranges, long kv_rows, int max_chunks, int causal,
+                  const void* ctx, const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk,
+                  long lddk, void* dv, long lddv, int B, int H, int Lq, int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(d_head == DH, FIRA_ERR_SHAPE, "attn_bwd: d_head %d != 32", d_head);
   FIRA_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lq <= LQ_MAX, FIRA_ERR_SHAPE, "attn_bwd: shape (Lq <= 32)");
   FIRA_CHECK_ARG(key_mask || ranges, FIRA_ERR_ARG, "attn_bwd: key_mask may only be NULL with ranges");
@@ -374,7 +374,7 @@ int attn_bwd_impl(const void* q, long ldq, const void* k, long ldk, const void* 
       (rc = check_layout("attn_bwd", v, ldv, dtype)) || (rc = check_layout("attn_bwd", ctx, ldo, dtype)) ||
       (rc = check_layout("attn_bwd", d_ctx, ldo, dtype)))
     return rc;
-  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv, ranges != nullptr) && (lddk % 8) == 0 && (lddv % 8) == 0 &&
+  if (use_tc(dtype, B, H, Lq, Lk, d_head, ldk, ldv, max_chunks) && (lddk % 8) == 0 && (lddv % 8) == 0 &&
       (lddq % 8) == 0)
     return fira_attn_tc_bwd(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, causal, ctx, d_ctx, ldo, stats, dq, lddq,
                             dk, lddk, dv, lddv, B, H, Lq, Lk, stream);
@@ -402,8 +402,8 @@ int fira_attn_fwd(const void* q, long ldq, const void* k, long ldk, const void* 
                   const unsigned char* key_mask, int causal, void* ctx, long ldo, float* stats, int B, int H, int Lq,
                   int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(key_mask, FIRA_ERR_ARG, "attn_fwd: null key_mask");
-  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, key_mask, nullptr, (long)B * Lk, causal, ctx, ldo, stats, B, H, Lq, Lk,
-                       d_head, dtype, stream);
+  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, key_mask, nullptr, (long)B * Lk, (Lk + 127) / 128, causal, ctx, ldo, stats,
+                       B, H, Lq, Lk, d_head, dtype, stream);
 }
 
 int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv,
@@ -411,25 +411,25 @@ int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* 
                   const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, int B, int H,
                   int Lq, int Lk, int d_head, int dtype, void* stream) {
   FIRA_CHECK_ARG(key_mask, FIRA_ERR_ARG, "attn_bwd: null key_mask");
-  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, key_mask, nullptr, (long)B * Lk, causal, ctx, d_ctx, ldo, stats, dq, lddq,
-                       dk, lddk, dv, lddv, B, H, Lq, Lk, d_head, dtype, stream);
+  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, key_mask, nullptr, (long)B * Lk, (Lk + 127) / 128, causal, ctx, d_ctx, ldo,
+                       stats, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, d_head, dtype, stream);
 }
 
 int fira_attn_packed_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
-                         long kv_rows, const unsigned char* key_mask, int mask_pitch, void* ctx, long ldo, float* stats,
-                         int B, int H, int Lq, int d_head, int dtype, void* stream) {
-  FIRA_CHECK_ARG(ranges && kv_rows > 0, FIRA_ERR_ARG, "attn_packed_fwd: ranges / kv_rows");
-  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, 0, ctx, ldo, stats, B, H, Lq, mask_pitch, d_head,
-                       dtype, stream);
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, int max_chunks, void* ctx, long ldo,
+                         float* stats, int B, int H, int Lq, int d_head, int dtype, void* stream) {
+  FIRA_CHECK_ARG(ranges && kv_rows > 0 && max_chunks > 0, FIRA_ERR_ARG, "attn_packed_fwd: ranges / kv_rows / max_chunks");
+  return attn_fwd_impl(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, max_chunks, 0, ctx, ldo, stats, B, H, Lq,
+                       mask_pitch, d_head, dtype, stream);
 }
 
 int fira_attn_packed_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
-                         long kv_rows, const unsigned char* key_mask, int mask_pitch, const void* ctx, const void* d_ctx,
-                         long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv,
-                         int B, int H, int Lq, int d_head, int dtype, void* stream) {
-  FIRA_CHECK_ARG(ranges && kv_rows > 0, FIRA_ERR_ARG, "attn_packed_bwd: ranges / kv_rows");
-  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, 0, ctx, d_ctx, ldo, stats, dq, lddq, dk, lddk,
-                       dv, lddv, B, H, Lq, mask_pitch, d_head, dtype, stream);
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, int max_chunks, const void* ctx,
+                         const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk,
+                         void* dv, long lddv, int B, int H, int Lq, int d_head, int dtype, void* stream) {
+  FIRA_CHECK_ARG(ranges && kv_rows > 0 && max_chunks > 0, FIRA_ERR_ARG, "attn_packed_bwd: ranges / kv_rows / max_chunks");
+  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, key_mask, ranges, kv_rows, max_chunks, 0, ctx, d_ctx, ldo, stats, dq, lddq,
+                       dk, lddk, dv, lddv, B, H, Lq, mask_pitch, d_head, dtype, stream);
 }
 
 }  // extern "C"

@@ -433,10 +433,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-// with ranges (two row ranges per commit, Lk = mask pitch >= their total) every range starts its own chunk:
-// ceil(l0/128) + ceil(l1/128) <= 3 is guaranteed when l0 + l1 <= 256
-inline bool eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges) {
-  return d_head == DH && H == 2 * HG && Lq >= 1 && Lq <= 32 && Lk >= 1 && Lk <= (ranges ? 2 : MAX_CH) * KC &&
+// max_chunks: 128-key chunks a commit needs (padded batches ceil(Lk / 128); packed batches every range starts its own
+// chunk, the caller passes the maximum over its commits); Lk = mask pitch
+inline bool eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, int max_chunks) {
+  return d_head == DH && H == 2 * HG && Lq >= 1 && Lq <= 32 && Lk >= 1 && Lk <= MAX_CH * KC && max_chunks <= MAX_CH &&
          (ldk % 8) == 0 && (ldv % 8) == 0;
 }
 
@@ -484,6 +484,6 @@ int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const voi
   return FIRA_OK;
 }
 
-bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, bool ranges) {
-  return attn_tc::eligible(B, H, Lq, Lk, d_head, ldk, ldv, ranges);
+bool fira_attn_tc_eligible(int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, int max_chunks) {
+  return attn_tc::eligible(B, H, Lq, Lk, d_head, ldk, ldv, max_chunks);
 }

@@ -189,18 +189,19 @@ int fira_host_packed_dims(const int* sou, const int* sub_token, const int* ast_c
   const int n0 = diff_len, n1 = sub_len, n2 = ast_change_len, N = n0 + n1 + n2;
   auto used = [](const int* row, int len) { int u = 0; for (int j = 0; j < len; ++j) if (row[j] != 0) u = j + 1; return u; };
   long rc = 0, rs = 0, ra = 0, nnz = 0;
-  int smax = 0;
+  int smax = 0, chmax = 0;
   for (int b = 0; b < batch; ++b) {
     const long i = index[b];
     const int uc = used(sou + i * n0, n0), us = used(sub_token + i * n1, n1), ua = used(ast_change + i * n2, n2);
     rc += uc; rs += us; ra += ua;
     smax = std::max(smax, uc + us);
+    chmax = std::max(chmax, (uc + 127) / 128 + (us + 127) / 128);        // 128-key chunks the attention kernel needs
     const unsigned char* d = deg + i * N;
     for (int j = 0; j < uc; ++j) nnz += d[j];
     for (int j = 0; j < us; ++j) nnz += d[n0 + j];
     for (int j = 0; j < ua; ++j) nnz += d[n0 + n1 + j];
   }
-  dims[0] = (int)rc; dims[1] = (int)rs; dims[2] = (int)ra; dims[3] = smax; dims[4] = (int)nnz;
+  dims[0] = (int)rc; dims[1] = (int)rs; dims[2] = (int)ra; dims[3] = smax; dims[4] = (int)nnz; dims[5] = chmax;
   return FIRA_OK;
 }
 

@@ -322,7 +322,7 @@ class PackedBatchLoader:
     is still visited exactly once per epoch, but batch composition is no longer independent of commit size."""
 
     def __init__(self, dataset, batch_size, vocab_size, shuffle=False, indices=None, multiples=(8, 8, 8),
-                 max_shapes=None, drop_last=False, prefetch=2, pin=None, bucket=0):
+                 max_shapes=None, drop_last=False, prefetch=2, pin=None, bucket=0, packed=False, row_buckets=None):
         self.ds, self.B, self.V = dataset, int(batch_size), int(vocab_size)
         self.shuffle, self.drop_last = shuffle, drop_last
         self.bucket = int(bucket)
@@ -347,7 +347,17 @@ class PackedBatchLoader:
         self.edge_cap = max(1, per_commit * self.B)
         self.pin = torch.cuda.is_available() if pin is None else pin
         self.n_slots = max(2, int(prefetch) + 1)
-        self.slots = [_Slot(self.B, self.lens, self.msg_len, self.edge_cap, self.pin) for _ in range(self.n_slots)]
+        # packed=True: per-commit packed batches (packed.PackedBatch) instead of batch-trimmed padded
+        # ones; row_buckets = rounding of (code rows, sub-token rows, AST rows, memory rows of one commit)
+        self.packed = bool(packed)
+        if self.packed:
+            from . import packed as P
+            self.tables = P.PackedTables(dataset)
+            self.row_buckets = tuple(row_buckets) if row_buckets else P.SEGMENT_BUCKETS
+            self.slots = [P.PackedSlot(self.B, self.lens, self.msg_len, self.edge_cap, self.pin)
+                          for _ in range(self.n_slots)]
+        else:
+            self.slots = [_Slot(self.B, self.lens, self.msg_len, self.edge_cap, self.pin) for _ in range(self.n_slots)]
 
     def __len__(self):
         n = len(self.indices)
@@ -360,6 +370,9 @@ class PackedBatchLoader:
             self.shapes[need] = self.shapes.get(need, 0) + 1
             return need
         fits = [s for s in self.shapes if all(a >= b for a, b in zip(s, need))]
+        if self.packed and not fits:                     # nothing emitted so far holds it: a new shape after all
+            self.shapes[need] = 1
+            return need
         best = min(fits, key=sum) if fits else self.lens
         self.shapes[best] = self.shapes.get(best, 0) + 1
         return best
@@ -369,6 +382,11 @@ class PackedBatchLoader:
         """index: int64 dataset positions -> batch (views of `slot`)."""
         slot = self.slots[0] if slot is None else slot
         index = np.ascontiguousarray(index, dtype=np.int64)
+        if self.packed:
+            from . import packed as P
+            need = self.tables.dims(index)
+            want = tuple(P._round_up(need[i], self.row_buckets[i]) for i in range(4))
+            return P.gather_packed(self.tables, index, self.V, slot, pad_dims=self._choose_dims(want))
         b = len(index)
         n0, n1, n2 = self.lens
         t = self.tab

@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from .graph import PackedEdges
+from .packed import PackedBatch
 from .parallel import FlatGradBucket
 
 ID_KEYS = ("sou", "tar", "mark", "ast_change", "tar_label", "sub_token")
@@ -43,6 +44,29 @@ class _Captured:
         self.B, self.n_nodes, self.cap = B, n_nodes, cap
         self.graph = None
         self.grads = None
+
+
+class _CapturedPacked:
+    """Static device copy of a per-commit packed batch shape (packed.PackedBatch) + its graph."""
+
+    def __init__(self, pb, cap, dev):
+        def z(t, n=None):
+            return torch.zeros(t.shape if n is None else (n,), dtype=t.dtype, device=dev)
+        t = {k: z(getattr(pb, k)) for k in PackedBatch.FIELDS if k not in ("col", "val")}
+        t["col"], t["val"] = z(pb.col, cap), z(pb.val, cap)
+        self.pb = PackedBatch(pb.B, pb.Rc, pb.Rs, pb.Ra, pb.S, pb.T, cap, pb.chunks, **t)
+        self.B, self.cap = pb.B, cap
+        self.graph = None
+        self.grads = None
+        self.packed = True
+
+    def copy_from(self, pb):
+        for k in PackedBatch.FIELDS:
+            src, dst = getattr(pb, k), getattr(self.pb, k)
+            if k in ("col", "val"):
+                dst[:src.numel()].copy_(src, non_blocking=True)
+            else:
+                dst.copy_(src, non_blocking=True)
 
 
 class GraphedTrainStep:
@@ -77,6 +101,16 @@ class GraphedTrainStep:
         """batch: [sou, tar, attr, mark, ast_change, edges, tar_label, sub_token]; `edges` a PackedEdges or a
         host/device (rowptr, col, val) triple.  Copies into the static buffers of the batch's shape
         (async when the sources are pinned) and makes that shape current."""
+        if isinstance(batch, PackedBatch):
+            if batch.nnz > self.cap:
+                raise ValueError(f"batch has {batch.nnz} edges, graph capacity is {self.cap}")
+            key = ("packed",) + batch.shape_key
+            c = self.captured.get(key)
+            if c is None:
+                c = self.captured[key] = _CapturedPacked(batch, self.cap, self.dev)
+            c.copy_from(batch)
+            self.cur = c
+            return c
         src, (rowptr, col, val) = self._split(batch)
         shapes = tuple(int(src[k].shape[1]) for k in ID_KEYS)
         B = int(src["sou"].shape[0])
@@ -106,7 +140,10 @@ class GraphedTrainStep:
     def _forward_backward(self, c):
         self.seed_ctr.add_(1)
         self.bucket.zero()
-        loss_sum, n_tok = self.model(*self._static_batch(c, c.B), "train")
+        if getattr(c, "packed", False):
+            loss_sum, n_tok = self.model.forward_packed(c.pb, "train")
+        else:
+            loss_sum, n_tok = self.model(*self._static_batch(c, c.B), "train")
         self.loss_sum.copy_(loss_sum.detach())
         self.n_local.copy_(n_tok)
         denom = self.n_global.squeeze(0) if self.world > 1 else n_tok.to(torch.float32)
@@ -114,8 +151,8 @@ class GraphedTrainStep:
 
     def _count_tokens_eager(self, c):
         if self.world > 1:
-            lab = c.ids["tar_label"]
-            self.n_global.copy_((lab[:, 1:] != 0).sum().to(torch.float32).reshape(1))
+            lab = c.pb.label if getattr(c, "packed", False) else c.ids["tar_label"][:, 1:]     # packed labels are shifted
+            self.n_global.copy_((lab != 0).sum().to(torch.float32).reshape(1))
             dist.all_reduce(self.n_global, group=self.group)
 
     def _eager_step(self, c):

@@ -552,7 +552,7 @@ class DecoderFn(torch.autograd.Function):
             st2 = torch.empty((B, H, T, 2), **f32)
             if pk is not None:
                 call("fira_attn_packed_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
-                     _ptr(pk.ranges), Ms, _ptr(mem_mask), S, _ptr(ctx2), D, _ptr(st2), B, H, T, D // H, pr.code, st)
+                     _ptr(pk.ranges), Ms, _ptr(mem_mask), S, pk.chunks, _ptr(ctx2), D, _ptr(st2), B, H, T, D // H, pr.code, st)
             else:
                 call("fira_attn_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
                      _ptr(mem_mask), 0, _ptr(ctx2), D, _ptr(st2), B, H, T, S, D // H, pr.code, st)
@@ -617,7 +617,7 @@ class DecoderFn(torch.autograd.Function):
             dQ = pr.empty((Mt, D), dev)
             if pk is not None:
                 call("fira_attn_packed_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
-                     _ptr(pk.ranges), Ms, _ptr(mem_mask), S, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D,
+                     _ptr(pk.ranges), Ms, _ptr(mem_mask), S, pk.chunks, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D,
                      _ptr(dKV, i * 2 * D), ldkv, _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, D // H, pr.code, st)
             else:
                 call("fira_attn_bwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,

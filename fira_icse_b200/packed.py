@@ -26,14 +26,17 @@ class PackedBatch:
     FIELDS = ("code", "mark", "pos", "sub", "ast", "off", "ranges", "mem_mask", "tar", "label", "tar_mask",
               "rowptr", "col", "val")
 
-    def __init__(self, B, Rc, Rs, Ra, S, T, nnz, **tensors):
+    def __init__(self, B, Rc, Rs, Ra, S, T, nnz, chunks=4, **tensors):
         self.B, self.Rc, self.Rs, self.Ra, self.S, self.T, self.nnz = B, Rc, Rs, Ra, S, T, nnz
+        # bound on the 128-key chunks cross-attention needs for any commit of the batch (3 on the whole shipped DataSet:
+        # <= 200 code tokens, <= 102 sub-tokens); part of the shape key because it selects the attention kernel
+        self.chunks = int(chunks)
         for k in self.FIELDS:
             setattr(self, k, tensors[k])
 
     @property
     def shape_key(self):
-        return (self.B, self.Rc, self.Rs, self.Ra, self.S)
+        return (self.B, self.Rc, self.Rs, self.Ra, self.S, self.chunks)
 
     @property
     def rows(self):
@@ -45,7 +48,7 @@ class PackedBatch:
 
     def to(self, device, non_blocking=True):
         t = {k: getattr(self, k).to(device, non_blocking=non_blocking) for k in self.FIELDS}
-        return PackedBatch(self.B, self.Rc, self.Rs, self.Ra, self.S, self.T, self.nnz, **t)
+        return PackedBatch(self.B, self.Rc, self.Rs, self.Ra, self.S, self.T, self.nnz, self.chunks, **t)
 
     def h2d_bytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size() for k in self.FIELDS)
@@ -73,10 +76,10 @@ class PackedTables:
         self.n = len(self.tab["sou"])
 
     def dims(self, index):
-        """-> (code rows, sub rows, AST rows, max memory rows of one commit, nnz) of the batch `index`"""
+        """-> (code rows, sub rows, AST rows, max memory rows of one commit, nnz, attention key chunks) of `index`"""
         index = np.ascontiguousarray(index, dtype=np.int64)
         t = self.tab
-        out = np.zeros(5, np.int32)
+        out = np.zeros(6, np.int32)
         host_call("fira_host_packed_dims", t["sou"].ctypes.data, t["sub_token"].ctypes.data, t["ast_change"].ctypes.data,
                   self.deg.ctypes.data, index.ctypes.data, len(index), *self.lens, out.ctypes.data)
         return tuple(int(x) for x in out)
@@ -112,8 +115,8 @@ def gather_packed(tables, index, vocab_size, slot, pad_dims=None, buckets=SEGMEN
     pad_dims: (Rc, Rs, Ra, S) to use (>= the batch's needs); default = the needs rounded up to `buckets`."""
     index = np.ascontiguousarray(index, dtype=np.int64)
     b = len(index)
+    need = tables.dims(index)
     if pad_dims is None:
-        need = tables.dims(index)
         pad_dims = tuple(_round_up(need[i], buckets[i]) for i in range(4))
     Rc, Rs, Ra, S = (int(x) for x in pad_dims)
     if Rc > slot.cap[0] or Rs > slot.cap[1] or Ra > slot.cap[2] or S > slot.cap[3]:
@@ -131,7 +134,7 @@ def gather_packed(tables, index, vocab_size, slot, pad_dims=None, buckets=SEGMEN
               slot.val.data_ptr(), slot.edge_cap, nnz.ctypes.data)
     e, T = int(nnz[0]), tables.msg_len
     slot.batch = PackedBatch(
-        b, Rc, Rs, Ra, S, T, e,
+        b, Rc, Rs, Ra, S, T, e, max(3, need[5]),
         code=slot.code[:Rc], mark=slot.mark[:Rc], pos=slot.pos[:Rc], sub=slot.sub[:Rs], ast=slot.ast[:Ra],
         off=slot.off[:3 * (b + 1)].view(3, b + 1), ranges=slot.ranges[:4 * b].view(b, 4),
         mem_mask=slot.mem_mask[:b * S].view(b, S), tar=slot.tar[:b * T].view(b, T), label=slot.label[:b * T].view(b, T),

@@ -164,14 +164,16 @@ int fira_attn_bwd(const void* q, long ldq, const void* k, long ldk, const void* 
 /* Cross-attention of a PACKED batch (fira_icse_b200/packed.py): the keys / values of commit b are two row ranges of
  * k / v, ranges[b] = {first row, rows, first row, rows} (code rows, sub-token rows; GLOBAL row ids, kv_rows = rows of
  * k / v), key_mask [B, mask_pitch] over the commit's own key positions (NULL: all valid), mask_pitch >= rows of any
- * commit.  Rows of dk / dv outside every range are not written (fira_zero_pad_rows clears the segment padding). */
+ * commit; max_chunks = an upper bound the caller guarantees on ceil(rows0 / 128) + ceil(rows1 / 128) of any commit
+ * (fira_host_packed_dims reports it; <= 3 lets bf16 run on the tcgen05 kernels).  Rows of dk / dv outside every range
+ * are not written (fira_zero_pad_rows clears the segment padding). */
 int fira_attn_packed_fwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
-                         long kv_rows, const unsigned char* key_mask, int mask_pitch, void* ctx, long ldo, float* stats,
-                         int B, int H, int Lq, int d_head, int dtype, void* stream);
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, int max_chunks, void* ctx, long ldo,
+                         float* stats, int B, int H, int Lq, int d_head, int dtype, void* stream);
 int fira_attn_packed_bwd(const void* q, long ldq, const void* k, long ldk, const void* v, long ldv, const int* ranges,
-                         long kv_rows, const unsigned char* key_mask, int mask_pitch, const void* ctx, const void* d_ctx,
-                         long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv,
-                         int B, int H, int Lq, int d_head, int dtype, void* stream);
+                         long kv_rows, const unsigned char* key_mask, int mask_pitch, int max_chunks, const void* ctx,
+                         const void* d_ctx, long ldo, const float* stats, void* dq, long lddq, void* dk, long lddk,
+                         void* dv, long lddv, int B, int H, int Lq, int d_head, int dtype, void* stream);
 
 /* ---- CopyNet scores (Model.py:17-18): sc[b,t,s] = b_res + w_res . tanh(src[b,s] + tgt[b,t]).
  *      src_mask [B,S] / row_mask [B*T] (optional, 1 = compute): positions the caller will mask anyway. */
@@ -244,7 +246,8 @@ int fira_host_gather_batch(const int* sou, const int* tar, const int* mark, cons
 /* fira_host_packed_dims / fira_host_gather_packed: the PER-COMMIT packed batch (replaces the
  *   fixed 210/160/280 padding of Dataset.py:80-94).  Per commit and segment only the positions up to the last non-zero
  *   id are kept; node rows are segment-major and ragged: [code rows of all commits | pad][sub-token rows | pad]
- *   [AST/edit rows | pad].  packed_dims -> dims[5] = {code rows, sub rows, AST rows, max memory rows of a commit, nnz}.
+ *   [AST/edit rows | pad].  packed_dims -> dims[6] = {code rows, sub rows, AST rows, max memory rows of a commit, nnz,
+ *   max over commits of ceil(code rows / 128) + ceil(sub rows / 128) = the key chunks fira_attn_packed_* needs}.
  *   gather_packed: pad_dims[4] = {Rc, Rs, Ra, S} buffer sizes (>= dims, bucketed by the caller); writes int32 node ids
  *   (o_code, o_mark, o_pos = position in the commit for the positional encoding; o_sub; o_ast), o_off[3][batch+1]
  *   (row offsets of each commit inside its segment), o_ranges[batch][4] = {first code row, code rows, first sub row
