@@ -70,9 +70,18 @@ class _CapturedPacked:
 
 
 class GraphedTrainStep:
-    def __init__(self, model, batch_size, optimizer_factory, edge_capacity=None, group=None):
+    def __init__(self, model, batch_size, optimizer_factory, edge_capacity=None, group=None, split=None):
         self.model, self.B, self.group = model, batch_size, group          # B: the largest batch (sizes the CSR capacity)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # split: capture the step as TWO graphs -- (A) forward + head/decoder backward down to the encoder memory,
+        # (B) encoder backward -- so that the all-reduce of the head/decoder gradients (3/4 of the bytes) runs on a
+        # communication stream WHILE graph B replays.  Default: on for N > 1 (FIRA_DP_OVERLAP=0 restores the single
+        # graph + one flat all-reduce); split=True on one GPU exercises the same two-graph path without NCCL (tests).
+        self.split = (self.world > 1 and os.environ.get("FIRA_DP_OVERLAP", "1") != "0") if split is None else bool(split)
+        self.comm = None
+        self._stash = None
+        self.flat_a = self.flat_b = None
+        self.params_a = self.params_b = None
         self.dev = next(model.parameters()).device
         self.cap = edge_capacity or batch_size * 4096
         self.n_global = torch.ones(1, dtype=torch.float32, device=self.dev)     # global token count (all ranks)
@@ -149,6 +158,70 @@ class GraphedTrainStep:
         denom = self.n_global.squeeze(0) if self.world > 1 else n_tok.to(torch.float32)
         (loss_sum / denom).backward()
 
+    # ------------------------------------------------------------------ split step (gradient all-reduce overlap)
+    def _split_memory(self, memory):
+        leaf = memory.detach().requires_grad_(True)
+        self._stash = (memory, leaf)
+        return leaf
+
+    def _phase_a(self, c):
+        """forward + backward of the head and the decoder; stops at the encoder memory (a leaf for this pass)"""
+        self.model._memory_hook = self._split_memory
+        try:
+            self._forward_backward(c)
+        finally:
+            self.model._memory_hook = None
+
+    def _phase_b(self):
+        """encoder backward from the memory gradient phase A left on the leaf"""
+        memory, leaf = self._stash
+        memory.backward(leaf.grad)
+
+    def _capture_split(self, c):
+        c.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(c.graph, pool=self.pool):
+            self._phase_a(c)
+        if self.params_a is None:
+            self.params_a = [p for p in self.bucket.params if p.grad is not None]
+            ids = {id(p) for p in self.params_a}
+            self.params_b = [p for p in self.bucket.params if id(p) not in ids]
+        c.grads_a = [p.grad for p in self.params_a]
+        c.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(c.graph_b, pool=self.pool):
+            self._phase_b()
+        c.grads_b = [p.grad for p in self.params_b]
+        assert all(g is not None for g in c.grads_a + c.grads_b), "a live parameter received no gradient"
+        if self.flat_a is None:
+            self.flat_a = torch.cat([g.reshape(-1) for g in c.grads_a])
+            self.flat_b = torch.cat([g.reshape(-1) for g in c.grads_b])
+            self.comm = torch.cuda.Stream()
+        for flat, params in ((self.flat_a, self.params_a), (self.flat_b, self.params_b)):
+            off = 0
+            for p in params:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        if self.graph_opt is None:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self.optimizer.step()
+
+    def _replay_split(self, c):
+        cur = torch.cuda.current_stream()
+        c.graph.replay()
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):               # head/decoder gradients: pack + all-reduce behind graph B
+            torch.cat([g.reshape(-1) for g in c.grads_a], out=self.flat_a)
+            if self.world > 1:
+                dist.all_reduce(self.flat_a, group=self.group)
+        c.graph_b.replay()
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            torch.cat([g.reshape(-1) for g in c.grads_b], out=self.flat_b)
+            if self.world > 1:
+                dist.all_reduce(self.flat_b, group=self.group)
+        cur.wait_stream(self.comm)
+        self.graph_opt.replay()
+
     def _count_tokens_eager(self, c):
         if self.world > 1:
             lab = c.pb.label if getattr(c, "packed", False) else c.ids["tar_label"][:, 1:]     # packed labels are shifted
@@ -178,6 +251,8 @@ class GraphedTrainStep:
         self.bucket.zero()
         if self.pool is None and os.environ.get("FIRA_GRAPH_PRIVATE_POOLS", "0") != "1":
             self.pool = torch.cuda.graph_pool_handle()
+        if self.split:
+            return self._capture_split(c)
         c.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(c.graph, pool=self.pool):
             self._forward_backward(c)
@@ -218,6 +293,10 @@ class GraphedTrainStep:
         if c.graph is None:
             self._capture(c)
         self._count_tokens_eager(c)
+        if self.split:
+            self._replay_split(c)
+            self.model.decoder.weights_epoch = getattr(self.model.decoder, "weights_epoch", 0) + 1
+            return self.loss_sum, self.n_local
         c.graph.replay()
         # graph replays update the parameters without touching their autograd version counters: tell weight caches
         # keyed on those (incremental.IncrementalDecoder) that the weights moved

@@ -62,6 +62,7 @@ class TransModel(nn.Module):
         self.out_fc = _OutFc(args.embedding_dim, args.vocab_size)
         self.gate_fc = nn.Linear(args.embedding_dim, 1)   # dead upstream too (Model.py:35)
         self.copy_net = CopyNet(args)
+        self._memory_hook = None      # engine.GraphedTrainStep(split=True): cuts the autograd graph at the encoder memory
         self.set_precision(os.environ.get("FIRA_PRECISION", "fp32"))
 
     def set_precision(self, precision):
@@ -95,6 +96,8 @@ class TransModel(nn.Module):
         pf_head = ops.prefetch_head(bf16, self.out_fc.weight, self.copy_net.LinearSource.weight,
                                     self.copy_net.LinearTarget.weight)
         memory = self.encoder.encode_memory_packed(pb)                       # [1, Rc + Rs, D]
+        if self._memory_hook is not None:
+            memory = self._memory_hook(memory)
         dec = self.decoder(pb.tar, memory, pb.mem_mask, pb.tar_mask, packed=pb)
         want_ids = stage != "train"
         loss_sum, _, ids = ops.HeadFn.apply(want_ids, bf16, pf_head, memory, dec, pb.mem_mask, pb.label.view(-1),
@@ -115,6 +118,8 @@ class TransModel(nn.Module):
         pf_head = ops.prefetch_head(bf16, self.out_fc.weight, self.copy_net.LinearSource.weight,
                                     self.copy_net.LinearTarget.weight) if sou.is_cuda else None
         memory = self.encoder.encode_memory(sou, mark, ast_change, edge, sub_token)
+        if self._memory_hook is not None:
+            memory = self._memory_hook(memory)
         dec = self.decoder(tar, memory, mem_mask, tar != 0)
         label = self.shifted_label(tar_label)
         want_ids = stage != "train"

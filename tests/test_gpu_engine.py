@@ -108,3 +108,64 @@ def test_multi_shape_graphs_share_one_pool_and_match_eager():
         if p.grad is None:
             continue
         assert torch.allclose(p, q, rtol=0, atol=5e-4), k
+
+
+def test_split_graphs_equal_the_single_graph_step():
+    """engine.GraphedTrainStep(split=True): graph A (forward + head/decoder backward) + graph B (encoder backward) +
+    optimizer graph -- the N > 1 path that overlaps the gradient all-reduce with graph B -- on one GPU (no NCCL) trains
+    exactly like the eager step"""
+    from fira_icse_b200.engine import GraphedTrainStep
+    from fira_icse_b200.parallel import DataParallelStep
+    base = copy.deepcopy(seeded_model()).to(DEV)
+    base.eval()
+    m_eager, m_graph = copy.deepcopy(base), copy.deepcopy(base)
+    batches = [_packed(i * 8, i * 8 + 8) for i in range(3)]
+    dp = DataParallelStep(m_eager, lambda ps: torch.optim.SGD(ps, lr=2e-3))
+    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=2e-3), split=True)
+    eng.load(batches[0])
+    eng.capture()
+    dp.step(batches[0])
+    for b in batches + batches:
+        loss_e, _ = dp.step(b)
+        ls, n = eng.step(b)
+        assert abs((ls / n).item() - loss_e.item()) <= 2e-4 * abs(loss_e.item())
+    assert eng.params_a and eng.params_b and len(eng.params_a) + len(eng.params_b) == len(eng.bucket.params)
+    names = {id(p): k for k, p in m_graph.named_parameters()}
+    assert all(names[id(p)].startswith("encoder.") for p in eng.params_b)
+    assert not any(names[id(p)].startswith("encoder.") for p in eng.params_a)
+    for (k, p), (_, q) in zip(m_eager.named_parameters(), m_graph.named_parameters()):
+        if p.grad is None:
+            continue
+        assert torch.allclose(p, q, rtol=0, atol=5e-4), k
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_packed_batches_through_the_graph_engine(split):
+    """per-commit packed batches (packed.PackedBatch) replayed as CUDA graphs == eager TransModel.forward_packed"""
+    import sys
+    from fira_icse_b200.engine import GraphedTrainStep
+    from fira_icse_b200.packed import PackedTables, pack_from_dataset
+    from test_packed import GoldenSplit, V
+    tables = PackedTables(GoldenSplit())
+    hosts = [pack_from_dataset(tables, np.arange(lo, lo + 8), V) for lo in (0, 8, 40)]
+    base = copy.deepcopy(seeded_model()).to(DEV)
+    base.eval()
+    m_eager, m_graph = copy.deepcopy(base), copy.deepcopy(base)
+    opt = torch.optim.SGD(m_eager.live_parameters(), lr=2e-3)
+    eng = GraphedTrainStep(m_graph, 8, lambda ps: torch.optim.SGD(ps, lr=2e-3), edge_capacity=32768, split=split)
+
+    def eager(pb):
+        opt.zero_grad(set_to_none=True)
+        ls, nt = m_eager.forward_packed(pb.to(DEV), "train")
+        loss = ls / nt
+        loss.backward()
+        opt.step()
+        return loss.item()
+    for k in [0, 1, 2, 0, 2, 1]:
+        le = eager(hosts[k])
+        ls, n = eng.step(hosts[k])
+        assert abs((ls / n).item() - le) <= 2e-4 * abs(le), (k, (ls / n).item(), le)
+    for (k, p), (_, q) in zip(m_eager.named_parameters(), m_graph.named_parameters()):
+        if p.grad is None:
+            continue
+        assert torch.allclose(p, q, rtol=0, atol=5e-4), k

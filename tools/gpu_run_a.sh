@@ -13,6 +13,8 @@ timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2a_bench_bf16.js
 FIRA_GCN_FUSED=1 timeout 900 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline > gpurun_out/r2a_bench_bf16_fused.json 2> gpurun_out/r2a_bench_bf16_fused.err
 FIRA_ATTN_TC=1 timeout 900 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline > gpurun_out/r2a_bench_bf16_attntc.json 2> gpurun_out/r2a_bench_bf16_attntc.err
 FIRA_ATTN_TC=1 FIRA_GCN_FUSED=1 timeout 900 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline > gpurun_out/r2a_bench_bf16_both.json 2> gpurun_out/r2a_bench_bf16_both.err
+timeout 900 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --layout packed > gpurun_out/r2a_bench_bf16_packed.json 2> gpurun_out/r2a_bench_bf16_packed.err
+FIRA_ATTN_TC=1 FIRA_GCN_FUSED=1 timeout 900 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --layout packed > gpurun_out/r2a_bench_bf16_packed_both.json 2> gpurun_out/r2a_bench_bf16_packed_both.err
 timeout 600 python bench.py --steps 20 --warmup 5 --precision fp32 --skip-cpu-baseline > gpurun_out/r2a_bench_fp32.json 2> gpurun_out/r2a_bench_fp32.err
 timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/r2a_bench_ref.json 2> gpurun_out/r2a_bench_ref.err
 tail -5 gpurun_out/r2a_pytest.log; tail -5 gpurun_out/r2a_pytest_gcn_fused.log; tail -5 gpurun_out/r2a_pytest_attn_tc.log; tail -5 gpurun_out/r2a_pytest_packed.log
