@@ -26,18 +26,19 @@ using namespace tc;
 
 constexpr int D = 256;
 constexpr int TM = 128;                    // rows per tile = UMMA M
-constexpr int N_EPI = 4, N_GATHER = 8;
-constexpr int WARP_MMA = N_EPI;            // warps 0-3 epilogue (TMEM lane quarters 0-3), 4 = TMA + MMA, 5-12 gather
+constexpr int N_EPI = 8, N_GATHER = 8;     // epilogue warp w: TMEM lane quarter w & 3, column half w >> 2
+constexpr int WARP_MMA = N_EPI;            // warps 0-7 epilogue, 8 = TMA + MMA, 9-16 gather
 constexpr int THREADS = (N_EPI + 1 + N_GATHER) * 32;
 constexpr int EC = 1024;                   // edges of a tile staged in shared memory (larger tiles read col/val from global)
 constexpr int STG_PITCH = 80;              // bytes per staged row of 32 bf16 (64 B) + 16 B pad: conflict-free 16-B accesses
 constexpr uint32_t B_BYTES = D * D * 2;    // 131072: 4 k-blocks x [256 n-rows x 128 B]
 constexpr uint32_t A_BYTES = TM * D * 2;   // 65536:  4 k-blocks x [128 rows x 128 B]
-constexpr uint32_t STG_BYTES = N_EPI * 2 * 32 * STG_PITCH;
+constexpr uint32_t STG_BYTES = N_EPI * 32 * STG_PITCH;          // per epilogue warp: one [32 x 32] bf16 block (in, then out)
 constexpr uint32_t OFF_A = B_BYTES, OFF_STG = OFF_A + A_BYTES, OFF_ROWPTR = OFF_STG + STG_BYTES,
                    OFF_COL = OFF_ROWPTR + 544, OFF_VAL = OFF_COL + EC * 4, OFF_RS = OFF_VAL + EC * 4,
-                   SMEM_BYTES = OFF_RS + 4 * TM * 4;
+                   OFF_ST = OFF_RS + 4 * TM * 4, SMEM_BYTES = OFF_ST + 2 * TM * 2 * 4;
 constexpr int GATHER_BAR = 1;              // named barrier of the gather warps
+constexpr int EPI_BAR = 2;                 // named barrier of the epilogue warps (row statistics exchange)
 
 struct Params {
   const int* rowptr; const int* col; const float* val;      // buffer-order CSR
@@ -79,6 +80,18 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+// 32 lanes x 32 consecutive fp32 columns back into TMEM (the layout tmem_ld32 reads)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_constant__ CUtensorMap tmW, Params p) {
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
       const bool staged = nE <= EC;
       if (staged)
         for (int i = gtid; i < nE; i += N_GATHER * 32) { s_col[i] = p.col[e_lo + i]; s_val[i] = p.val[e_lo + i]; }
-      if (t >= 1) mbar_wait(smem_addr(&a_empty), (t - 1) & 1);          // MMAs of tile t-1 have read the A tile
+      if (t >= 1 && gtid == 0) mbar_wait(smem_addr(&a_empty), (t - 1) & 1);   // MMAs of tile t-1 have read the A tile
       asm volatile("bar.sync %0, %1;" ::"n"(GATHER_BAR), "n"(N_GATHER * 32) : "memory");
       const int* cp = staged ? s_col : p.col + e_lo;
       const float* vp = staged ? s_val : p.val + e_lo;
@@ -221,121 +234,163 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
       mbar_arrive(smem_addr(&a_full));
     }
   } else {
-    // ======================================================= epilogue warps (TMEM lanes 32*warp .. +31)
-    unsigned char* stg_in = sm + OFF_STG + warp * 2 * 32 * STG_PITCH;     // residual / addend chunk, 32 rows x 64 B
-    unsigned char* stg_out = stg_in + 32 * STG_PITCH;
+    // ======================================================= epilogue warps: TMEM lanes 32*(warp & 3), columns 128*(warp >> 2)
+    // Per warp and 32-column chunk: the residual / addend block [32 rows x 32 cols] is fetched one chunk AHEAD into
+    // registers (coalesced 64-B row segments), handed over through a staging block (lane = row afterwards); results go
+    // back through a second staging block so that global stores are 64-B row segments too.  MODE 0 keeps
+    // y = dropout(z) + h in TMEM (tcgen05.st) between the statistics pass and the normalisation pass.
+    const int quarter = warp & 3, half = warp >> 2;
+    unsigned char* stg = sm + OFF_STG + warp * 32 * STG_PITCH;
     const float* s_rs = reinterpret_cast<const float*>(sm + OFF_RS);
+    float* s_st = reinterpret_cast<float*>(sm + OFF_ST);                 // [2 halves][128 rows][sum, sumsq]
     uint64_t seed = p.seed;
     if (MODE == 0 && p.seed_ctr) seed += *p.seed_ctr;
     const float keep_scale = (MODE == 0 && p.p_drop > 0.f) ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int lrow = lane >> 2, lch = lane & 3;      // cooperative 64-B row segments: 8 rows x 4 chunks per pass
+    const int lrow = lane >> 2, lch = lane & 3;      // cooperative 64-B row segments: 8 rows x 4 chunks per instruction
+    const __nv_bfloat16* resid = MODE == 0 ? p.x : p.addend;
     for (int t = 0; t < ntiles; ++t) {
       long r0; int rows, nt_;
       tile_range(p.R, cta, ncta, t, r0, rows, nt_);
       const int buf = t & 1;
-      mbar_wait(smem_addr(&tmem_full[buf]), (t >> 1) & 1);
-      tc_fence_after();
-      const int wrow0 = warp * 32;                   // first tile row of this warp
+      const int wrow0 = quarter * 32;                // first tile row of this warp
       const int my = wrow0 + lane;                   // this thread's tile row
       const bool live = my < rows;
       const long grow = r0 + my;
-      const uint32_t tacc = tmem_base + buf * D + ((uint32_t)wrow0 << 16);
-      const __nv_bfloat16* resid = MODE == 0 ? p.x : p.addend;
-      float rs = 0.f, sum = 0.f, sq = 0.f, mean = 0.f, rstd = 0.f;
+      const uint32_t tacc = tmem_base + buf * D + ((uint32_t)wrow0 << 16) + half * 128;
+      const int col0 = half * 128;
+      // prefetch of the first residual chunk can start before the accumulator is ready
+      uint4 pre[4];
+      auto fetch = [&](int k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + lrow;
+          pre[i] = make_uint4(0, 0, 0, 0);
+          if (wrow0 + rr < rows && resid != nullptr)
+            pre[i] = __ldg(reinterpret_cast<const uint4*>(resid + (r0 + wrow0 + rr) * D + col0 + k * 32 + lch * 8));
+        }
+      };
+      fetch(0);
+      if (lane == 0) mbar_wait(smem_addr(&tmem_full[buf]), (t >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      float rs = 0.f, sum = 0.f, sq = 0.f;
       if (MODE == 0 && live) rs = s_rs[(t & 3) * TM + my];
-      const int npass = MODE == 0 ? 2 : 1;
 #pragma unroll 1
-      for (int pass = 0; pass < npass; ++pass) {
-#pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
-          // residual / addend chunk [32 rows x 32 cols] -> staging (coalesced 64-B segments)
+      for (int k = 0; k < 4; ++k) {
+        const int c = col0 + k * 32;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = i * 8 + lrow;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (wrow0 + rr < rows && (MODE == 0 || resid != nullptr))
-              v = *reinterpret_cast<const uint4*>(resid + (r0 + wrow0 + rr) * D + c * 32 + lch * 8);
-            *reinterpret_cast<uint4*>(stg_in + rr * STG_PITCH + lch * 16) = v;
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (i * 8 + lrow) * STG_PITCH + lch * 16) = pre[i];
+        if (k < 3) fetch(k + 1);
+        uint32_t acc[32];
+        tmem_ld32(tacc + k * 32, acc);
+        __syncwarp();
+        uint4 hp[4];                                 // this thread's row of the residual block, still packed
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + j * 16);
+        __syncwarp();                                // the block is free: it takes the results now
+        float y[32];
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c + j));
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(p.c1 + c + j));
+            y[j + 0] = fmaf(rs, cv.x, __uint_as_float(acc[j + 0]) + bv.x);
+            y[j + 1] = fmaf(rs, cv.y, __uint_as_float(acc[j + 1]) + bv.y);
+            y[j + 2] = fmaf(rs, cv.z, __uint_as_float(acc[j + 2]) + bv.z);
+            y[j + 3] = fmaf(rs, cv.w, __uint_as_float(acc[j + 3]) + bv.w);
           }
+          // Z is stored as bf16 and the LayerNorm backward recomputes from the stored value: normalise the same value
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 zp = pack8(y + j * 8);
+            *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + j * 16) = zp;
+            unpack8(zp, y + j * 8);
+          }
+          if (p.p_drop > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t m = dropout_keep8(seed, p.stream_id, (uint64_t)grow * 32 + (c >> 3) + j, p.p_drop);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[j * 8 + i] = ((m >> i) & 1) ? y[j * 8 + i] * keep_scale : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float h[8];
+            unpack8(hp[j], h);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float v = y[j * 8 + i] + h[i]; y[j * 8 + i] = v; sum += v; sq = fmaf(v, v, sq); }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(y[j]);
+          tmem_st32(tacc + k * 32, acc);             // y stays in TMEM for the normalisation pass
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float h[8];
+            unpack8(hp[j], h);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[j * 8 + i] = __uint_as_float(acc[j * 8 + i]) + h[i];
+            *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + j * 16) = pack8(y + j * 8);
+          }
+        }
+        __syncwarp();
+        // staged [32 x 32] bf16 block (Z, or dH) -> global, 64-B row segments
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + lrow;
+          if (wrow0 + rr < rows) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * STG_PITCH + lch * 16);
+            __nv_bfloat16* dst = MODE == 0 ? p.z : p.y;
+            *reinterpret_cast<uint4*>(dst + (r0 + wrow0 + rr) * D + c + lch * 8) = v;
+          }
+        }
+        __syncwarp();
+      }
+      if (MODE == 0) {
+        tmem_st_wait();
+        // row statistics over all 256 columns: the two warps of a lane quarter exchange their halves
+        s_st[(half * TM + my) * 2] = sum;
+        s_st[(half * TM + my) * 2 + 1] = sq;
+        asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR), "n"(N_EPI * 32) : "memory");
+        const float tsum = sum + s_st[((half ^ 1) * TM + my) * 2];
+        const float tsq = sq + s_st[((half ^ 1) * TM + my) * 2 + 1];
+        const float mean = tsum * (1.f / D);
+        const float var = fmaxf(tsq * (1.f / D) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + kLnEps);
+        if (live && half == 0 && p.mean) { p.mean[grow] = mean; p.rstd[grow] = rstd; }
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int c = col0 + k * 32;
           uint32_t acc[32];
-          tmem_ld32(tacc + c * 32, acc);
-          __syncwarp();
-          float h[32];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) unpack8(*reinterpret_cast<const uint4*>(stg_in + lane * STG_PITCH + j * 16), h + j * 8);
+          tmem_ld32(tacc + k * 32, acc);
           float o[32];
-          if (MODE == 0) {
-            float y[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + j));
-              const float4 cv = __ldg(reinterpret_cast<const float4*>(p.c1 + c * 32 + j));
-              y[j + 0] = fmaf(rs, cv.x, __uint_as_float(acc[j + 0]) + bv.x);
-              y[j + 1] = fmaf(rs, cv.y, __uint_as_float(acc[j + 1]) + bv.y);
-              y[j + 2] = fmaf(rs, cv.z, __uint_as_float(acc[j + 2]) + bv.z);
-              y[j + 3] = fmaf(rs, cv.w, __uint_as_float(acc[j + 3]) + bv.w);
-            }
-            // Z is stored as bf16 and the LayerNorm backward recomputes from the stored value: normalise the same value
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __bfloat162float(__float2bfloat16_rn(y[j]));
-            if (pass == 0) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg_out + lane * STG_PITCH + j * 16) = pack8(y + j * 8);
-            }
-            if (p.p_drop > 0.f) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t m = dropout_keep8(seed, p.stream_id, (uint64_t)grow * 32 + c * 4 + j, p.p_drop);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[j * 8 + i] = ((m >> i) & 1) ? y[j * 8 + i] * keep_scale : 0.f;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] += h[j];
-            if (pass == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { sum += y[j]; sq = fmaf(y[j], y[j], sq); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 gv = __ldg(reinterpret_cast<const float4*>(p.gamma + c * 32 + j));
-                const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + c * 32 + j));
-                o[j + 0] = fmaf((y[j + 0] - mean) * rstd, gv.x, bt.x);
-                o[j + 1] = fmaf((y[j + 1] - mean) * rstd, gv.y, bt.y);
-                o[j + 2] = fmaf((y[j + 2] - mean) * rstd, gv.z, bt.z);
-                o[j + 3] = fmaf((y[j + 3] - mean) * rstd, gv.w, bt.w);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg_out + lane * STG_PITCH + j * 16) = pack8(o + j * 8);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(acc[j]) + h[j];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg_out + lane * STG_PITCH + j * 16) = pack8(o + j * 8);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(p.gamma + c + j));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + c + j));
+            o[j + 0] = fmaf((__uint_as_float(acc[j + 0]) - mean) * rstd, gv.x, bt.x);
+            o[j + 1] = fmaf((__uint_as_float(acc[j + 1]) - mean) * rstd, gv.y, bt.y);
+            o[j + 2] = fmaf((__uint_as_float(acc[j + 2]) - mean) * rstd, gv.z, bt.z);
+            o[j + 3] = fmaf((__uint_as_float(acc[j + 3]) - mean) * rstd, gv.w, bt.w);
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + j * 16) = pack8(o + j * 8);
           __syncwarp();
-          // staged [32 x 32] bf16 block -> global, 64-B row segments
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = i * 8 + lrow;
             if (wrow0 + rr < rows) {
               const long gr = r0 + wrow0 + rr;
-              const uint4 v = *reinterpret_cast<const uint4*>(stg_out + rr * STG_PITCH + lch * 16);
-              __nv_bfloat16* dst;
-              if (MODE == 0) dst = pass == 0 ? p.z : (gr < p.split ? p.outA : p.outB);
-              else dst = p.y;
-              *reinterpret_cast<uint4*>(dst + gr * D + c * 32 + lch * 8) = v;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * STG_PITCH + lch * 16);
+              __nv_bfloat16* dst = gr < p.split ? p.outA : p.outB;
+              *reinterpret_cast<uint4*>(dst + gr * D + c + lch * 8) = v;
             }
           }
           __syncwarp();
         }
-        if (MODE == 0 && pass == 0) {
-          mean = sum * (1.f / D);
-          const float var = fmaxf(sq * (1.f / D) - mean * mean, 0.f);
-          rstd = rsqrtf(var + kLnEps);
-          if (live && p.mean) { p.mean[grow] = mean; p.rstd[grow] = rstd; }
-        }
+        // the partner warp must have read s_st before the next tile overwrites it
+        asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR), "n"(N_EPI * 32) : "memory");
       }
       tc_fence_before();
       mbar_arrive(smem_addr(&tmem_empty[buf]));

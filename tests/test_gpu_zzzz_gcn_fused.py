@@ -203,7 +203,8 @@ def test_encoder_with_fused_gcn_matches_unfused_path():
     assert abs(l0 - l1) <= 5e-3 * abs(l0), (l0, l1)
     worst = 1.0
     for k in g0:
-        if g0[k].norm().item() < 1e-6:
+        # fc_k.bias / LinearRes.bias: zero in exact arithmetic (softmax shift invariance), round-off noise here
+        if g0[k].norm().item() < 1e-6 or k.endswith("fc_k.bias") or k.endswith("LinearRes.bias"):
             continue
         c = float((g0[k].double().flatten() @ g1[k].double().flatten()) / (g0[k].double().norm() * g1[k].double().norm()))
         worst = min(worst, c)
