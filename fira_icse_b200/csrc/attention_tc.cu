@@ -85,13 +85,61 @@ __device__ __forceinline__ void make_chunks(Chunks& ch, const int* ranges, int b
   ch.nch = n;
 }
 
-// score of key i of a chunk for query t from the raw accumulator value (mpos = the key's mask position)
-__device__ __forceinline__ float masked_score(float raw, float scale, int i, int n_keys, int mpos, int t, int causal,
-                                              const unsigned char* s_mask) {
-  if (i >= n_keys) return -INFINITY;                 // tile overrun: not a key of this commit at all
-  const bool masked = s_mask[mpos] == 0 || (causal && mpos > t);
-  return masked ? kMaskFill : raw * scale;
+// Key validity as bit masks, one word per 32-key group of a chunk:
+//   exist[c*4+j] bit i : key j*32+i of chunk c is a key of this commit (below the chunk's key count)
+//   bits [c*4+j] bit i : ... and its mask byte is set
+// A chunk without a single valid key is DROPPED from the table when the commit has valid keys elsewhere (its
+// probabilities and gradients are exactly zero: exp(-1e9 - max) == 0 in fp32); `rm` keeps the dropped chunks so that
+// the backward can write their zero dK / dV rows.  A commit / row without any valid key keeps everything: every score
+// is -1e9 there and the softmax is uniform over ALL keys, like the reference's masked_fill + softmax.
+struct KeyBits { uint32_t bits[MAX_CH * 4]; uint32_t exist[MAX_CH * 4]; };
+
+__device__ __forceinline__ void prepare_keys(Chunks& ch, Chunks& rm, KeyBits& kb, const unsigned char* s_mask, int causal,
+                                             int warp, int lane) {
+  if (warp == 0) {
+    unsigned has = 0;
+    for (int c = 0; c < ch.nch; ++c) {
+      bool v = false;
+      for (int i = lane; i < ch.n[c]; i += 32) v |= s_mask[ch.moff[c] + i] != 0;
+      if (__any_sync(0xffffffffu, v)) has |= 1u << c;
+    }
+    if (lane == 0) {
+      int k = 0, r = 0;
+      const bool drop = has != 0 && !causal;
+      for (int c = 0; c < ch.nch; ++c) {
+        if (!drop || ((has >> c) & 1)) { ch.row[k] = ch.row[c]; ch.n[k] = ch.n[c]; ch.moff[k] = ch.moff[c]; ++k; }
+        else { rm.row[r] = ch.row[c]; rm.n[r] = ch.n[c]; rm.moff[r] = ch.moff[c]; ++r; }
+      }
+      ch.nch = k; rm.nch = r;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < ch.nch * KC; idx += THREADS) {       // THREADS % 32 == 0: a warp covers one group
+    const int c = idx >> 7, i = idx & 127;
+    const bool ex = i < ch.n[c];
+    const bool ok = ex && s_mask[ch.moff[c] + i] != 0;
+    const unsigned bv = __ballot_sync(0xffffffffu, ok), be = __ballot_sync(0xffffffffu, ex);
+    if (lane == 0) { kb.bits[idx >> 5] = bv; kb.exist[idx >> 5] = be; }
+  }
+  __syncthreads();
 }
+
+// valid keys of group j of chunk c for query row t
+__device__ __forceinline__ uint32_t row_bits(const KeyBits& kb, const Chunks& ch, int c, int j, int t, int causal) {
+  uint32_t v = kb.bits[c * 4 + j];
+  if (causal) {                                     // key position <= t (causal attention has one chunk, moff = 0)
+    const int lo = ch.moff[c] + j * 32;
+    v &= t < lo ? 0u : (t - lo >= 31 ? 0xffffffffu : ((2u << (t - lo)) - 1u));
+  }
+  return v;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
 
 // =================================================================================================== forward
 // smem: A'(Q) 32 KB | KV[3] 96 KB | P[2] 64 KB
@@ -101,7 +149,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __shared__ __align__(8) unsigned long long kv_full[MAX_CH], v_full[MAX_CH], s_full, p_full[2], p_empty[2], o_full;
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned char s_mask[MAX_CH * KC];
-  __shared__ Chunks ch;
+  __shared__ Chunks ch, rm;
+  __shared__ KeyBits kb;
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* sm = smem_raw + (base - smem_addr(smem_raw));
   constexpr uint32_t OFF_AQ = 0, OFF_KV = TILE, OFF_P = OFF_KV + MAX_CH * TILE;
@@ -125,6 +174,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  prepare_keys(ch, rm, kb, s_mask, a.causal, warp, lane);
   const int nch = ch.nch;
   if (warp == 4 && lane == 0) {                      // K chunks can fly while the A' tile is built
     for (int c = 0; c < nch; ++c) {
@@ -146,11 +196,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         mbar_wait(smem_addr(&kv_full[c]), 0);
         tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
+        for (int kb_ = 0; kb_ < 2; ++kb_)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + c * KC, make_desc(base + OFF_AQ + kb * PANEL + k * 32, 16, 1024),
-                      make_desc(base + OFF_KV + c * TILE + kb * PANEL + k * 32, 16, 1024), idesc_s, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem + c * KC, make_desc(base + OFF_AQ + kb_ * PANEL + k * 32, 16, 1024),
+                      make_desc(base + OFF_KV + c * TILE + kb_ * PANEL + k * 32, 16, 1024), idesc_s, (kb_ | k) ? 1u : 0u);
       }
       umma_commit(smem_addr(&s_full));
       mbar_wait(smem_addr(&s_full), 0);               // the K tiles have been read: reuse their buffers for V
@@ -180,36 +230,53 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     const int t = lane;
     const bool live = t < a.Lq;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    mbar_wait(smem_addr(&s_full), 0);
+    // does this row see any valid key at all?  (no: every score is -1e9 -> uniform over all existing keys)
+    uint32_t any = 0;
+    for (int c = 0; c < nch; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) any |= row_bits(kb, ch, c, j, t, a.causal);
+    const bool rowfilled = any == 0;
+    if (lane == 0) mbar_wait(smem_addr(&s_full), 0);
+    __syncwarp();
     tc_fence_after();
-    float mx = -INFINITY;
+    // pass A: row maximum of the raw scores over the valid keys (the scale is positive)
+    float mraw = -INFINITY;
     for (int c = 0; c < nch; ++c)
 #pragma unroll 1
-      for (int j = 0; j < KC / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(trow + c * KC + j * 32, r);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t vb = row_bits(kb, ch, c, j, t, a.causal);
+        if (__any_sync(0xffffffffu, vb != 0)) {       // warp-uniform: tcgen05.ld is .sync.aligned
+          uint32_t r[32];
+          tmem_ld32(trow + c * KC + j * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          mx = fmaxf(mx, masked_score(__uint_as_float(r[i]), a.scale, j * 32 + i, ch.n[c], ch.moff[c] + j * 32 + i, t,
-                                      a.causal, s_mask));
+          for (int i = 0; i < 32; ++i) if ((vb >> i) & 1) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+        }
       }
+    const float mx = rowfilled ? kMaskFill : mraw * a.scale;            // what the reference's softmax subtracts
+    const float k2 = a.scale * kLog2e, m2 = mraw * k2;
     float sum = 0.f;
+    const int m = warp * 32 + lane;
     for (int c = 0; c < nch; ++c) {
-      if (c >= 2) mbar_wait(smem_addr(&p_empty[c & 1]), ((c >> 1) - 1) & 1);
+      if (c >= 2) { if (lane == 0) mbar_wait(smem_addr(&p_empty[c & 1]), ((c >> 1) - 1) & 1); __syncwarp(); }
       unsigned char* ptile = sm + OFF_P + (c & 1) * TILE;
-      const int m = warp * 32 + lane;
 #pragma unroll 1
-      for (int j = 0; j < KC / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(trow + c * KC + j * 32, r);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t vb = row_bits(kb, ch, c, j, t, a.causal), eb = kb.exist[c * 4 + j];
         float e[32];
+        if (__any_sync(0xffffffffu, vb != 0 && !rowfilled)) {
+          uint32_t r[32];
+          tmem_ld32(trow + c * KC + j * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = masked_score(__uint_as_float(r[i]), a.scale, j * 32 + i, ch.n[c], ch.moff[c] + j * 32 + i, t,
-                                       a.causal, s_mask);
-          // the MMA consumes bf16(e): sum the ROUNDED values so that P rows are normalised exactly
-          const float ev = live ? __bfloat162float(__float2bfloat16_rn(expf(s - mx))) : 0.f;
-          e[i] = ev; sum += ev;
+          for (int i = 0; i < 32; ++i) {
+            // the MMA consumes bf16(e): sum the ROUNDED values so that P rows are normalised exactly
+            const float x = rowfilled ? (((eb >> i) & 1) ? 1.f : 0.f)
+                                      : (((vb >> i) & 1) ? fast_exp2(fmaf(__uint_as_float(r[i]), k2, -m2)) : 0.f);
+            e[i] = live ? __bfloat162float(__float2bfloat16_rn(x)) : 0.f;
+            sum += e[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { e[i] = (live && rowfilled && ((eb >> i) & 1)) ? 1.f : 0.f; sum += e[i]; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -224,7 +291,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       fence_proxy_async();
       mbar_arrive(smem_addr(&p_full[c & 1]));
     }
-    mbar_wait(smem_addr(&o_full), 0);
+    if (lane == 0) mbar_wait(smem_addr(&o_full), 0);
+    __syncwarp();
     tc_fence_after();
     uint32_t r[32];
     tmem_ld32(trow + MAX_CH * KC + warp * DH, r);      // own head's 32 output columns
@@ -257,7 +325,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __shared__ __align__(8) unsigned long long kv_full, s_full, ds_full, g_full, epi_done;
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned char s_mask[MAX_CH * KC];
-  __shared__ Chunks ch;
+  __shared__ Chunks ch, rm;
+  __shared__ KeyBits kb;
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* sm = smem_raw + (base - smem_addr(smem_raw));
   constexpr uint32_t OFF_AQ = 0, OFF_ADO = TILE, OFF_K = 2 * TILE, OFF_V = 3 * TILE, OFF_P = 4 * TILE, OFF_DS = 5 * TILE;
@@ -267,6 +336,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   if (threadIdx.x == 0) {
     make_chunks(ch, a.ranges, b, a.Lk);
+    rm.nch = 0;
     mbar_init(smem_addr(&kv_full), 1);
     mbar_init(smem_addr(&s_full), 1);
     mbar_init(smem_addr(&ds_full), 128);
@@ -283,7 +353,24 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  prepare_keys(ch, rm, kb, s_mask, a.causal, warp, lane);
   const int nch = ch.nch;
+  if (warp == 4 && lane == 0 && nch > 0) {           // the first K / V chunk flies while the A' tiles are built
+    const uint32_t bar = smem_addr(&kv_full);
+    mbar_expect_tx(bar, 2 * TILE);
+    tma_load_2d(base + OFF_K, &tmK, g * GF, ch.row[0], bar);
+    tma_load_2d(base + OFF_K + PANEL, &tmK, g * GF + 64, ch.row[0], bar);
+    tma_load_2d(base + OFF_V, &tmV, g * GF, ch.row[0], bar);
+    tma_load_2d(base + OFF_V + PANEL, &tmV, g * GF + 64, ch.row[0], bar);
+  }
+  // dropped chunks (no valid key, the commit has valid keys elsewhere): their dK / dV rows are exactly zero
+  for (int c = 0; c < rm.nch; ++c)
+    for (int i = threadIdx.x; i < rm.n[c] * (GF / 8); i += THREADS) {
+      const int r = i / (GF / 8), q = i % (GF / 8);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(a.dk + (long)(rm.row[c] + r) * a.lddk + g * GF + q * 8) = z;
+      *reinterpret_cast<uint4*>(a.dv + (long)(rm.row[c] + r) * a.lddv + g * GF + q * 8) = z;
+    }
   build_masked_tile(sm + OFF_AQ, a.q, a.ldq, b, g, a.Lq, threadIdx.x, THREADS);
   __syncthreads();
   build_masked_tile(sm + OFF_ADO, a.d_ctx, a.ldo, b, g, a.Lq, threadIdx.x, THREADS);
@@ -296,23 +383,25 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, GF, false, true);       // dQ     : K-major A (dS), MN-major B (K)
       constexpr uint32_t idesc_nn = make_idesc_bf16(128, GF, true, true);        // dK, dV : MN-major A (dS^T / P^T), MN-major B (A')
       for (int c = 0; c < nch; ++c) {
-        if (c >= 1) mbar_wait(smem_addr(&epi_done), (c - 1) & 1);   // dK/dV of the previous chunk read out; K/V/P/dS free
         const uint32_t bar = smem_addr(&kv_full);
-        mbar_expect_tx(bar, 2 * TILE);
-        tma_load_2d(base + OFF_K, &tmK, g * GF, ch.row[c], bar);
-        tma_load_2d(base + OFF_K + PANEL, &tmK, g * GF + 64, ch.row[c], bar);
-        tma_load_2d(base + OFF_V, &tmV, g * GF, ch.row[c], bar);
-        tma_load_2d(base + OFF_V + PANEL, &tmV, g * GF + 64, ch.row[c], bar);
+        if (c >= 1) {
+          mbar_wait(smem_addr(&epi_done), (c - 1) & 1); // dK/dV of the previous chunk read out; K/V/P/dS free
+          mbar_expect_tx(bar, 2 * TILE);
+          tma_load_2d(base + OFF_K, &tmK, g * GF, ch.row[c], bar);
+          tma_load_2d(base + OFF_K + PANEL, &tmK, g * GF + 64, ch.row[c], bar);
+          tma_load_2d(base + OFF_V, &tmV, g * GF, ch.row[c], bar);
+          tma_load_2d(base + OFF_V + PANEL, &tmV, g * GF + 64, ch.row[c], bar);
+        }
         mbar_wait(bar, c & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
+        for (int kb_ = 0; kb_ < 2; ++kb_)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem + T_S, make_desc(base + OFF_AQ + kb * PANEL + k * 32, 16, 1024),
-                      make_desc(base + OFF_K + kb * PANEL + k * 32, 16, 1024), idesc_kk, (kb | k) ? 1u : 0u);
-            umma_bf16(tmem + T_DP, make_desc(base + OFF_ADO + kb * PANEL + k * 32, 16, 1024),
-                      make_desc(base + OFF_V + kb * PANEL + k * 32, 16, 1024), idesc_kk, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem + T_S, make_desc(base + OFF_AQ + kb_ * PANEL + k * 32, 16, 1024),
+                      make_desc(base + OFF_K + kb_ * PANEL + k * 32, 16, 1024), idesc_kk, (kb_ | k) ? 1u : 0u);
+            umma_bf16(tmem + T_DP, make_desc(base + OFF_ADO + kb_ * PANEL + k * 32, 16, 1024),
+                      make_desc(base + OFF_V + kb_ * PANEL + k * 32, 16, 1024), idesc_kk, (kb_ | k) ? 1u : 0u);
           }
         umma_commit(smem_addr(&s_full));
         mbar_wait(smem_addr(&ds_full), c & 1);         // P and dS of this chunk are in shared memory, S / dP consumed
@@ -336,6 +425,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     const int t = lane, m = warp * 32 + lane;
     const bool live = t < a.Lq;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t any = 0;
+    for (int c = 0; c < nch; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) any |= row_bits(kb, ch, c, j, t, a.causal);
+    const bool rowfilled = any == 0;
     // delta = dO . O over the own head's 32 features; row statistics
     float delta = 0.f, mx = 0.f, inv = 0.f;
     if (live) {
@@ -352,23 +446,30 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       const float* st = a.stats + (((long)b * a.H + g * HG + warp) * a.Lq + t) * 2;
       mx = st[0]; inv = 1.f / st[1];
     }
+    const float k2 = a.scale * kLog2e, m2 = mx * kLog2e;
     for (int c = 0; c < nch; ++c) {
-      mbar_wait(smem_addr(&s_full), c & 1);
+      if (lane == 0) mbar_wait(smem_addr(&s_full), c & 1);
+      __syncwarp();
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < KC / 32; ++j) {
-        uint32_t rs[32], rp[32];
-        tmem_ld32(trow + T_S + j * 32, rs);
-        tmem_ld32(trow + T_DP + j * 32, rp);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t vb = row_bits(kb, ch, c, j, t, a.causal), eb = kb.exist[c * 4 + j];
         float pv[32], dsv[32];
+        if (__any_sync(0xffffffffu, vb != 0 && !rowfilled)) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(trow + T_S + j * 32, rs);
+          tmem_ld32(trow + T_DP + j * 32, rp);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ki = j * 32 + i, mpos = ch.moff[c] + ki;
-          const float s = masked_score(__uint_as_float(rs[i]), a.scale, ki, ch.n[c], mpos, t, a.causal, s_mask);
-          const bool masked = ki >= ch.n[c] || s_mask[mpos] == 0 || (a.causal && mpos > t);
-          const float p = live ? expf(s - mx) * inv : 0.f;                 // exp(-inf) = 0 beyond Lk
-          pv[i] = p;
-          dsv[i] = masked ? 0.f : p * (__uint_as_float(rp[i]) - delta) * a.scale;   // masked_fill blocks the gradient
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = live && !rowfilled && ((vb >> i) & 1);
+            const float p = ok ? fast_exp2(fmaf(__uint_as_float(rs[i]), k2, -m2)) * inv
+                               : ((live && rowfilled && ((eb >> i) & 1)) ? inv : 0.f);
+            pv[i] = p;
+            dsv[i] = ok ? p * (__uint_as_float(rp[i]) - delta) * a.scale : 0.f;      // masked_fill blocks the gradient
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { pv[i] = (live && rowfilled && ((eb >> i) & 1)) ? inv : 0.f; dsv[i] = 0.f; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -390,7 +491,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       fence_proxy_async();
       mbar_arrive(smem_addr(&ds_full));
       // ---- dK, dV rows of this chunk: thread = key row (warp*32 + lane), 128 features of the group
-      mbar_wait(smem_addr(&g_full), c & 1);
+      if (lane == 0) mbar_wait(smem_addr(&g_full), c & 1);
+      __syncwarp();
       tc_fence_after();
       const int ki = warp * 32 + lane;                 // key row of this chunk
 #pragma unroll 1
@@ -416,14 +518,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     }
     // ---- dQ: own head's 32 columns (the scale is already folded into dS)
     uint32_t r[32];
-    tmem_ld32(trow + T_DQ + warp * DH, r);
+    if (nch > 0) tmem_ld32(trow + T_DQ + warp * DH, r);
     if (live) {
       __nv_bfloat16* dst = a.dq + ((long)b * a.Lq + t) * a.lddq + g * GF + warp * DH;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(r[q * 8 + i]);
+        for (int i = 0; i < 8; ++i) o[i] = nch > 0 ? __uint_as_float(r[q * 8 + i]) : 0.f;
         Act<__nv_bfloat16>::store8(dst + q * 8, o);
       }
     }
