@@ -526,7 +526,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FIRA_PRECISION", "bf16"), choices=["bf16", "fp32"],
                     help="bf16 = BASELINE.json config (default); fp32 = parity mode")
-    ap.add_argument("--layout", default=os.environ.get("FIRA_LAYOUT", "trimmed"), choices=["trimmed", "packed"],
+    ap.add_argument("--layout", default=os.environ.get("FIRA_LAYOUT", "packed"), choices=["trimmed", "packed"],
                     help="trimmed = padded batches cut to the batch maximum; packed = per-commit packed node rows")
     ap.add_argument("--no-trim", dest="trim", action="store_false",
                     help="feed fully padded 210/160/280 batches instead of loader-trimmed ones")
@@ -535,6 +535,8 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling runs only (ncu): leave out the host-CPU leg")
     args = ap.parse_args()
+    if not args.graph and args.layout == "packed":
+        args.layout = "trimmed"                      # eager launches (profiling runs): the padded layout
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -106,16 +106,17 @@ __device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, 
 }
 // keep-mask for 8 consecutive elements starting at element index idx8*8.
 // Returns an 8-bit mask; element i kept iff bit i set.  p_drop in [0,1).
+// ONE Philox4x32-7 call serves the 8 elements: 16 random bits per element, compared against p with 2^-16 resolution
+// (p = 0.1 -> 0.100006, p = 0.2 -> 0.199997).  Every dropout site (LayerNorm blocks, Combination gate, fused GCN
+// epilogue) and its backward draw their masks through this one function, so they agree by construction.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t idx8, float p_drop) {
-  uint4 r0 = philox4((uint32_t)idx8, (uint32_t)(idx8 >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  uint4 r1 = philox4((uint32_t)idx8, (uint32_t)(idx8 >> 32), stream, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  // compare the top 24 bits against p (uniform in [0,1) with 2^-24 resolution)
-  const uint32_t thr = (uint32_t)(p_drop * 16777216.0f);
+  const uint4 r = philox4((uint32_t)idx8, (uint32_t)(idx8 >> 32), stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t thr = (uint32_t)(p_drop * 65536.0f);
   uint32_t m = 0;
-  m |= ((r0.x >> 8) >= thr) << 0; m |= ((r0.y >> 8) >= thr) << 1;
-  m |= ((r0.z >> 8) >= thr) << 2; m |= ((r0.w >> 8) >= thr) << 3;
-  m |= ((r1.x >> 8) >= thr) << 4; m |= ((r1.y >> 8) >= thr) << 5;
-  m |= ((r1.z >> 8) >= thr) << 6; m |= ((r1.w >> 8) >= thr) << 7;
+  m |= ((r.x & 0xffffu) >= thr) << 0; m |= ((r.x >> 16) >= thr) << 1;
+  m |= ((r.y & 0xffffu) >= thr) << 2; m |= ((r.y >> 16) >= thr) << 3;
+  m |= ((r.z & 0xffffu) >= thr) << 4; m |= ((r.z >> 16) >= thr) << 5;
+  m |= ((r.w & 0xffffu) >= thr) << 6; m |= ((r.w >> 16) >= thr) << 7;
   return m;
 }
 

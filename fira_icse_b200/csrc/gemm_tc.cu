@@ -327,12 +327,9 @@ int make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, i
 template <int BN, int STAGES>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
-    attr = true;
-  }
+  // per launch, not cached in a static: the attribute is per device, and a static flag would be shared state
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
   gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
   return FIRA_OK;
@@ -362,7 +359,16 @@ extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const vo
   FIRA_CHECK_ARG((rs == nullptr) == (rc == nullptr), FIRA_ERR_ARG, "gemm_bf16_tc: rs/rc must come together");
   FIRA_CHECK_ARG(!(splits > 1 && (c_is_bf16 || relu)), FIRA_ERR_ARG, "gemm_bf16_tc: split-K needs fp32 C and no relu");
   cudaStream_t st = (cudaStream_t)stream;
-  const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  // Tile width: 256 columns per CTA amortise the A tile best, but a product with few row tiles (the decoder's
+  // M = B*30 = 15 tiles) then runs on 15-60 SMs and each CTA carries a 128 x 256 epilogue.  Narrower tiles spread such
+  // products over more SMs: the smallest width whose grid still fits one wave (148 CTAs) wins.
+  int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  {
+    const long mt = (M + BM - 1) / BM;
+    const int sp = splits < 1 ? 1 : splits;
+    for (int cand = 64; cand < BN; cand *= 2)
+      if (mt * ((N + cand - 1) / cand) * sp <= 148) { BN = cand; break; }
+  }
   CUtensorMap ta, tb;
   int rc_;
   // A: K-major -> matrix [M rows, K cols], box {64 k, 128 m};  MN-major -> matrix [K rows, M cols], box {64 m, 64 k}

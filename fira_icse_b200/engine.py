@@ -69,6 +69,24 @@ class _CapturedPacked:
                 dst.copy_(src, non_blocking=True)
 
 
+class _OptimizerPair:
+    """the two optimizers of the overlapped step behind the one-optimizer interface callers use (step / state_dict)"""
+
+    def __init__(self, pair):
+        self.pair = pair
+
+    def step(self):
+        for o in self.pair:
+            o.step()
+
+    def zero_grad(self, set_to_none=True):
+        for o in self.pair:
+            o.zero_grad(set_to_none=set_to_none)
+
+    def state_dict(self):
+        return [o.state_dict() for o in self.pair]
+
+
 class GraphedTrainStep:
     def __init__(self, model, batch_size, optimizer_factory, edge_capacity=None, group=None, split=None):
         self.model, self.B, self.group = model, batch_size, group          # B: the largest batch (sizes the CSR capacity)
@@ -82,6 +100,12 @@ class GraphedTrainStep:
         self._stash = None
         self.flat_a = self.flat_b = None
         self.params_a = self.params_b = None
+        # one GPU: two optimizers (head/decoder parameters, encoder parameters) so that the first can step while the
+        # encoder backward still runs (FIRA_OPT_OVERLAP=0: one optimizer at the end of the graph)
+        self.opt_factory = optimizer_factory
+        self.opt_pair = None
+        self.opt_stream = None
+        self.opt_overlap = self.world == 1 and not self.split and os.environ.get("FIRA_OPT_OVERLAP", "1") != "0"
         self.dev = next(model.parameters()).device
         self.cap = edge_capacity or batch_size * 4096
         self.n_global = torch.ones(1, dtype=torch.float32, device=self.dev)     # global token count (all ranks)
@@ -231,6 +255,21 @@ class GraphedTrainStep:
     def _eager_step(self, c):
         """A normal (uncaptured) training step: initialises the optimizer state and all lazy CUDA state."""
         self._count_tokens_eager(c)
+        if self.opt_overlap and self.opt_pair is None:
+            # find the two parameter groups with one split backward, then train with two optimizers from the start
+            self._phase_a(c)
+            pa = [p for p in self.bucket.params if p.grad is not None]
+            ids = {id(p) for p in pa}
+            pb = [p for p in self.bucket.params if id(p) not in ids]
+            self._phase_b()
+            self.params_a, self.params_b = pa, pb
+            self.opt_pair = (self.opt_factory(pa), self.opt_factory(pb))
+            self.optimizer = _OptimizerPair(self.opt_pair)
+            self.opt_stream = torch.cuda.Stream()
+            self.opt_pair[0].step()
+            self.opt_pair[1].step()
+            self.opt_ready = True
+            return
         self._forward_backward(c)
         if self.world > 1:
             self.bucket.all_reduce(self.group)
@@ -255,9 +294,21 @@ class GraphedTrainStep:
             return self._capture_split(c)
         c.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(c.graph, pool=self.pool):
-            self._forward_backward(c)
-            if self.world == 1:
-                self.optimizer.step()
+            if self.world == 1 and self.opt_pair is not None:
+                # ONE graph, two branches: Adam on the head/decoder parameters (3/4 of the bytes, memory-bound, nothing
+                # else could hide it at the end of the step) runs on a side stream WHILE the encoder backward runs
+                self._phase_a(c)
+                cur = torch.cuda.current_stream()
+                self.opt_stream.wait_stream(cur)
+                with torch.cuda.stream(self.opt_stream):
+                    self.opt_pair[0].step()
+                self._phase_b()
+                cur.wait_stream(self.opt_stream)
+                self.opt_pair[1].step()
+            else:
+                self._forward_backward(c)
+                if self.world == 1:
+                    self.optimizer.step()
         if self.world > 1:
             # the captured backward always writes the same pool tensors; pack them into ONE static flat buffer
             # (eager concat + NCCL all-reduce) and let the captured optimizer read views of that buffer

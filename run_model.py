@@ -158,7 +158,7 @@ def train_epoch(dp, model, train_loader, epoch, best_bleu, dev_loader, g, valid_
         else:
             loss, _ = dp.step(batch_to_device(batch, dev_))
             total_loss += loss.item()
-        total_data += len(batch[0]) * WORLD
+        total_data += (batch.B if hasattr(batch, "shape_key") else len(batch[0])) * WORLD
         if idx % 10 == 0 and RANK == 0:
             print("epoch: %d batch: %d/%d  data: %d/%d loss: %.4f" % (
                 epoch, idx, len(train_loader), total_data, n_train_total(train_loader) * WORLD, float(total_loss) / 10))
@@ -188,7 +188,10 @@ def main_train():
         train_loader = PackedBatchLoader(train_set, args.batch_size, args.vocab_size, shuffle=True,
                                          indices=range(lo, hi) if WORLD > 1 else None, multiples=(8, 16, 16),
                                          max_shapes=int(os.environ.get("FIRA_MAX_SHAPES", 24)), drop_last=WORLD > 1,
-                                         bucket=int(os.environ.get("FIRA_BUCKET", 0)))
+                                         bucket=int(os.environ.get("FIRA_BUCKET", 0)),
+                                         # per-commit packed node rows (packed.py) by default; FIRA_LAYOUT=trimmed keeps
+                                         # the padded batches cut to the batch maximum
+                                         packed=os.environ.get("FIRA_LAYOUT", "packed") == "packed")
         dp = GraphedTrainStep(model, args.batch_size, lambda ps: Adam(ps, args.lr, fused=True, capturable=True),
                               edge_capacity=train_loader.edge_cap)
     else:

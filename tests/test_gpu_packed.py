@@ -76,7 +76,8 @@ def test_packed_bf16_mode_matches_padded_bf16_mode(model):
     assert n_pad == n_pk and abs(l_pad - l_pk) <= 2e-3 * abs(l_pad), (l_pad, l_pk)
     for k in g_pad:
         a, b = g_pad[k].double().flatten(), g_pk[k].double().flatten()
-        if a.norm().item() < 1e-6:
+        # fc_k.bias / LinearRes.bias vanish in exact arithmetic (softmax shift invariance): round-off noise
+        if a.norm().item() < 1e-6 or k.endswith("fc_k.bias") or k.endswith("LinearRes.bias"):
             continue
         cos = float((a @ b) / (a.norm() * b.norm()))
         assert cos > 0.995, (k, cos)

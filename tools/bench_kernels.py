@@ -19,18 +19,31 @@ DEV = "cuda:0"
 BF = torch.bfloat16
 
 
-def timeit(fn, iters=20, warm=5):
+def timeit(fn, reps=10, iters=10, warm=3):
+    """GPU time per call: `reps` back-to-back launches captured into ONE CUDA graph (no host launch overhead between
+    them, the way the training step replays them), replayed `iters` times between CUDA events."""
     for _ in range(warm):
         fn()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     torch.cuda.synchronize()
     for a, b in ev:
         a.record()
-        fn()
+        g.replay()
         b.record()
     torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    return {"avg_us": 1e3 * sum(ms) / len(ms), "min_us": 1e3 * ms[0], "med_us": 1e3 * ms[len(ms) // 2]}
+    us = sorted(1e3 * a.elapsed_time(b) / reps for a, b in ev)
+    return {"avg_us": sum(us) / len(us), "min_us": us[0], "med_us": us[len(us) // 2], "timing": f"{reps} launches per graph replay"}
 
 
 def st():
