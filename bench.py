@@ -246,6 +246,64 @@ def spmm_roofline(dev, hb, B, bf16=False):
             "l2": f"cold: {n_pairs} rotating buffer pairs ({n_pairs * 2 * R * 256 * esz / 1e6:.0f} MB > 126 MB L2)"}
 
 
+# ------------------------------------------------------------------------------------------------ fused GCN roofline
+def gcn_fused_roofline(dev, pb):
+    """The fused GCN layer kernel (fira_gcn_layer_fwd: gather -> tcgen05 -> bias/rowsum/dropout/residual/LayerNorm out of
+    TMEM, ONE launch) timed alone with CUDA events on the node rows / adjacency of a packed bench batch `pb` (device),
+    cold L2 (rotating buffer sets larger than the 126 MB L2).  Algorithmic bytes = SURVEY.md 8d's fused formula: read H
+    once + write the layer output once + rowptr + (col, val) + the weight once per launch; the kernel also writes Z (the
+    pre-LayerNorm rows the backward needs) -- reported separately, not counted as algorithmic."""
+    import torch
+    from fira_icse_b200 import _lib
+    R, Mc = pb.rows, pb.Rc
+    n_sets = max(3, int(400e6 // (3 * R * 256 * 2)) + 1)
+    bf = torch.bfloat16
+    hs = [torch.randn(R, 256, device=dev).to(bf) for _ in range(n_sets)]
+    zs = [torch.empty(R, 256, device=dev, dtype=bf) for _ in range(n_sets)]
+    oa = [torch.empty(Mc, 256, device=dev, dtype=bf) for _ in range(n_sets)]
+    ob = [torch.empty(R, 256, device=dev, dtype=bf) for _ in range(n_sets)]
+    W = (torch.randn(256, 256, device=dev) / 16).to(bf)
+    b2, c1 = torch.randn(256, device=dev) * 0.1, torch.randn(256, device=dev) * 0.1
+    gamma, beta = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    stats = torch.empty(2, R, device=dev)
+    st = torch.cuda.current_stream()
+
+    def launch(i):
+        k = i % n_sets
+        _lib.call("fira_gcn_layer_fwd", pb.rowptr.data_ptr(), pb.col.data_ptr(), pb.val.data_ptr(), hs[k].data_ptr(),
+                  W.data_ptr(), b2.data_ptr(), c1.data_ptr(), gamma.data_ptr(), beta.data_ptr(), zs[k].data_ptr(),
+                  oa[k].data_ptr(), ob[k].data_ptr(), Mc, stats.data_ptr(), stats.data_ptr() + 4 * R, R, 256, 0.2, 1234, None,
+                  2, st.cuda_stream)
+    for i in range(6):
+        launch(i)
+    iters = 40
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for i in range(iters):
+        ev[i][0].record(st)
+        launch(i)
+        ev[i][1].record(st)
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    avg_ms = sum(ms) / len(ms)
+    nnz = int(pb.nnz)
+    alg_bytes = 2 * R * 256 * 2 + (R + 1) * 4 + nnz * 8 + 256 * 256 * 2
+    peak, how = measured_peaks()
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("fira_gcn_layer_fwd_dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": "gcn_fused_kernel<0> (fira_gcn_layer_fwd: gather -> tcgen05.mma -> LayerNorm epilogue)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": alg_bytes, "bytes_incl_saved_z": alg_bytes + R * 256 * 2,
+            "avg_launch_ms": avg_ms, "median_launch_ms": ms[len(ms) // 2], "launches_timed": iters, "rows": R, "nnz": nnz,
+            "peak_source": how, "dtype": "bf16",
+            "shape": "node rows / adjacency of one packed bench batch (per-commit packed layout)",
+            "l2": f"cold: {n_sets} rotating buffer sets ({n_sets * 4 * R * 256 * 2 / 1e6:.0f} MB > 126 MB L2)",
+            "note": "timed with events around one launch from Python: includes the launch gap (~2-3 us at this size)"}
+
+
 # ------------------------------------------------------------------------------------------------ GEMM roofline
 def gemm_roofline(dev, B):
     """The kernel with the largest share of the bf16 step is the tcgen05 GEMM; time its most frequent large
@@ -471,6 +529,21 @@ def run_gpu_arm(args):
     roof = spmm_roofline(dev, full_host, B, bf16=args.precision == "bf16")
     roof_f32 = spmm_roofline(dev, full_host, B, bf16=False) if args.precision == "bf16" else None
     roof_gemm = gemm_roofline(dev, B) if args.precision == "bf16" else None
+    roof_fused = None
+    if args.precision == "bf16":
+        if packed:
+            roof_fused = gcn_fused_roofline(dev, pool_dev[0])
+        else:
+            from fira_icse_b200.packed import PackedTables, pack_from_dataset
+            from fira_icse_b200.synth import SynthDataset
+            import numpy as np
+            roof_fused = gcn_fused_roofline(dev, pack_from_dataset(
+                PackedTables(SynthDataset(rank * N_POOL * B, B, VOCAB, AST_VOCAB)), np.arange(B), VOCAB).to(dev))
+        if os.environ.get("FIRA_GCN_FUSED", "0") != "0":
+            # the GNN message passing of the timed step IS this kernel: it is the headline roofline then
+            roof, roof_scatter_bf16 = roof_fused, roof
+        else:
+            roof_scatter_bf16 = None
 
     # ---- CPU baseline on this box's host cores: the unmodified reference, same batch (bounded sample)
     cpu_info = None
@@ -511,7 +584,7 @@ def run_gpu_arm(args):
             "e2e_loader": loader_info,
             "e2e_dense_edge": dense_info,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_scatter_fp32": roof_f32,
-            "roofline_gemm": roof_gemm,
+            "roofline_gemm": roof_gemm, "roofline_gcn_fused": roof_fused,
             "cpu_baseline": cpu_info, "last_loss": last_loss[0]}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -105,7 +105,7 @@ class GraphedTrainStep:
         self.opt_factory = optimizer_factory
         self.opt_pair = None
         self.opt_stream = None
-        self.opt_overlap = self.world == 1 and not self.split and os.environ.get("FIRA_OPT_OVERLAP", "1") != "0"
+        self.opt_overlap = self.world == 1 and not self.split and os.environ.get("FIRA_OPT_OVERLAP", "0") != "0"
         self.dev = next(model.parameters()).device
         self.cap = edge_capacity or batch_size * 4096
         self.n_global = torch.ones(1, dtype=torch.float32, device=self.dev)     # global token count (all ranks)
@@ -199,6 +199,9 @@ class GraphedTrainStep:
     def _phase_b(self):
         """encoder backward from the memory gradient phase A left on the leaf"""
         memory, leaf = self._stash
+        # drop the reference BEFORE anything else can run: a stashed autograd graph keeps the parameters' AccumulateGrad
+        # nodes alive, and a later (captured) forward would re-use nodes bound to the stream of THIS pass
+        self._stash = None
         memory.backward(leaf.grad)
 
     def _capture_split(self, c):
@@ -278,6 +281,7 @@ class GraphedTrainStep:
 
     def _capture(self, c):
         """Warm the shape up with one forward/backward whose gradients are discarded, then capture."""
+        self._stash = None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
