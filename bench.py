@@ -521,6 +521,26 @@ def run_gpu_arm(args):
                       "note": "eager (no CUDA graph); edge passed as the reference's dense float64 [B,650,650] host "
                               "tensor (Dataset.py:340)"}
 
+    # ---- the fp32 parity mode (logits within 1e-4 of the reference) on the same batches: an extra key of the bf16 line
+    parity_info = None
+    if args.precision == "bf16" and args.graph and world == 1 and not args.skip_parity_mode:
+        m32 = F.TransModel(model_args()).to(dev)
+        m32.load_state_dict(model.state_dict())
+        m32.train()
+        m32.set_precision("fp32")
+        eng32 = GraphedTrainStep(m32, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True),
+                                 edge_capacity=eng.cap)
+        for hb in pool_dev:
+            eng32.step(hb)
+        for hb in pool_dev:
+            eng32.step(hb)
+        k32 = max(4, min(10, args.steps))
+        ms32 = timed(lambda i: eng32.step(pool_dev[i % N_POOL]), k32)
+        parity_info = {"value": B * k32 / (ms32 * 1e-3), "unit": "commits/s", "ms_per_step": ms32 / k32, "steps": k32,
+                       "precision_mode": "fp32 parity (fp32 storage, fp32 FFMA GEMMs): loss / logits within 1e-4 of the reference"}
+        del eng32, m32
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -585,6 +605,7 @@ def run_gpu_arm(args):
             "e2e_dense_edge": dense_info,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_scatter_fp32": roof_f32,
             "roofline_gemm": roof_gemm, "roofline_gcn_fused": roof_fused,
+            "fp32_parity_mode": parity_info,
             "cpu_baseline": cpu_info, "last_loss": last_loss[0]}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -605,6 +626,7 @@ def main():
                     help="feed fully padded 210/160/280 batches instead of loader-trimmed ones")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--skip-parity-mode", action="store_true", help="leave out the fp32 parity-mode extra key")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling runs only (ncu): leave out the host-CPU leg")
     args = ap.parse_args()

@@ -30,8 +30,8 @@ namespace {
 // bf16 activations go to the tensor-core kernels unless FIRA_ATTN_TC=0 (A/B runs against the FFMA kernels below)
 bool use_tc(int dtype, int B, int H, int Lq, int Lk, int d_head, long ldk, long ldv, int max_chunks) {
   if (dtype != FIRA_BF16 || !fira_attn_tc_eligible(B, H, Lq, Lk, d_head, ldk, ldv, max_chunks)) return false;
-  const char* e = getenv("FIRA_ATTN_TC");
-  return e ? atoi(e) != 0 : false;      // TODO default on once validated on the GPU
+  const char* e = getenv("FIRA_ATTN_TC");      // read per call: an A/B switch, not cached process state
+  return e ? atoi(e) != 0 : true;
 }
 
 constexpr int DH = 32;           // head dim (256 / 8)
