@@ -258,36 +258,27 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
       const long grow = r0 + my;
       const uint32_t tacc = tmem_base + buf * D + ((uint32_t)wrow0 << 16) + half * 128;
       const int col0 = half * 128;
-      // prefetch of the first residual chunk can start before the accumulator is ready
-      uint4 pre[4];
-      auto fetch = [&](int k) {
+      // residual / addend: every thread reads ITS row directly (16-B loads, two 32-column chunks ahead in registers);
+      // the first two chunks are requested before the accumulator is ready, so their latency hides behind the MMAs
+      uint4 hq[2][4];
+      auto fetch = [&](int k, uint4* dst) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = i * 8 + lrow;
-          pre[i] = make_uint4(0, 0, 0, 0);
-          if (wrow0 + rr < rows && resid != nullptr)
-            pre[i] = __ldg(reinterpret_cast<const uint4*>(resid + (r0 + wrow0 + rr) * D + col0 + k * 32 + lch * 8));
+        for (int j = 0; j < 4; ++j) {
+          dst[j] = make_uint4(0, 0, 0, 0);
+          if (live && resid != nullptr) dst[j] = __ldg(reinterpret_cast<const uint4*>(resid + grow * D + col0 + k * 32 + j * 8));
         }
       };
-      fetch(0);
+      fetch(0, hq[0]);
+      fetch(1, hq[1]);
       if (lane == 0) mbar_wait(smem_addr(&tmem_full[buf]), (t >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       float rs = 0.f, sum = 0.f, sq = 0.f;
       if (MODE == 0 && live) rs = s_rs[(t & 3) * TM + my];
-#pragma unroll 1
-      for (int k = 0; k < 4; ++k) {
+      auto chunk = [&](int k, const uint4* hp) {
         const int c = col0 + k * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (i * 8 + lrow) * STG_PITCH + lch * 16) = pre[i];
-        if (k < 3) fetch(k + 1);
         uint32_t acc[32];
         tmem_ld32(tacc + k * 32, acc);
-        __syncwarp();
-        uint4 hp[4];                                 // this thread's row of the residual block, still packed
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hp[j] = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + j * 16);
-        __syncwarp();                                // the block is free: it takes the results now
         float y[32];
         if (MODE == 0) {
 #pragma unroll
@@ -346,6 +337,13 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
           }
         }
         __syncwarp();
+      };
+#pragma unroll 1
+      for (int k = 0; k < 4; k += 2) {
+        chunk(k, hq[0]);
+        if (k + 2 < 4) fetch(k + 2, hq[0]);
+        chunk(k + 1, hq[1]);
+        if (k + 3 < 4) fetch(k + 3, hq[1]);
       }
       if (MODE == 0) {
         tmem_st_wait();
