@@ -466,6 +466,19 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        resident_step(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_step": True, "value": value, "ms_per_step": ms / args.steps,
+                              "launches_per_step": launches_per_step}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end-to-end arm: pinned host batch -> H2D -> TransModel.forward -> backward -> Adam -> loss D2H
     for i in range(min(3, args.warmup)):
         e2e_step(i)
@@ -629,6 +642,9 @@ def main():
     ap.add_argument("--skip-parity-mode", action="store_true", help="leave out the fp32 parity-mode extra key")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling runs only (ncu): leave out the host-CPU leg")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="profiling runs only (ncu --profile-from-start off): after the timed region, ONE more step "
+                         "between cudaProfilerStart/Stop, then exit without the extra legs")
     args = ap.parse_args()
     if not args.graph and args.layout == "packed":
         args.layout = "trimmed"                      # eager launches (profiling runs): the padded layout
