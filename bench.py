@@ -466,6 +466,26 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
+    if args.timeline:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(3):
+                resident_step(i)
+                torch.cuda.synchronize()
+        if rank == 0:
+            prof.export_chrome_trace(args.timeline)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import timeline_summary as TS
+            steps = TS.split_steps(TS.load(args.timeline), 3)
+            with open(args.timeline + ".summary.txt", "w") as f:
+                print(json.dumps({"value": value, "ms_per_step": ms / args.steps}), file=f)
+                TS.summarize(steps[1], out=f)
+            print(json.dumps({"timeline": args.timeline, "value": value, "ms_per_step": ms / args.steps}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     if args.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -642,6 +662,10 @@ def main():
     ap.add_argument("--skip-parity-mode", action="store_true", help="leave out the fp32 parity-mode extra key")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="profiling runs only (ncu): leave out the host-CPU leg")
+    ap.add_argument("--timeline", default=None,
+                    help="profiling runs only: after the timed region, 3 more steps under torch.profiler (CUPTI kernel "
+                         "activity); writes the chrome trace to this path and its summary (tools/timeline_summary.py) "
+                         "next to it, then exits")
     ap.add_argument("--profile-step", action="store_true",
                     help="profiling runs only (ncu --profile-from-start off): after the timed region, ONE more step "
                          "between cudaProfilerStart/Stop, then exit without the extra legs")

@@ -112,6 +112,7 @@ constexpr int PAIRS_MAX = (LQ_MAX / 2 + NWARPS - 1) / NWARPS;      // query-row 
 template <typename T>
 __global__ void __launch_bounds__(NTHR) attn_fwd_kernel(AttnArgs a, T* __restrict__ ctx, long ldo,
                                                         float* __restrict__ stats /* [B,H,Lq,2] */) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   extern __shared__ float smem[];
   __shared__ int nv_s, filled_s;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(NTHR) attn_bwd_kernel(AttnArgs a, const T* __r
                                                         long ldo, const float* __restrict__ stats, T* __restrict__ dq,
                                                         long lddq, T* __restrict__ dk, long lddk, T* __restrict__ dv,
                                                         long lddv) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   extern __shared__ float smem[];
   __shared__ int nv_s, filled_s;
   __shared__ float delta_s[LQ_MAX], mx_s[LQ_MAX], inv_s[LQ_MAX];
@@ -352,10 +354,10 @@ int attn_fwd_impl(const void* q, long ldq, const void* k, long ldk, const void* 
   const size_t smem = fwd_smem(Lq, Lk);
   if (dtype == FIRA_F32) {
     if ((rc = set_smem(attn_fwd_kernel<float>, smem, "attn_fwd"))) return rc;
-    attn_fwd_kernel<float><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(a, (float*)ctx, ldo, stats);
+    launch_k(attn_fwd_kernel<float>, dim3(B * H), dim3(NTHR), smem, (cudaStream_t)stream, a, (float*)ctx, ldo, stats);
   } else {
     if ((rc = set_smem(attn_fwd_kernel<__nv_bfloat16>, smem, "attn_fwd"))) return rc;
-    attn_fwd_kernel<__nv_bfloat16><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)ctx, ldo, stats);
+    launch_k(attn_fwd_kernel<__nv_bfloat16>, dim3(B * H), dim3(NTHR), smem, (cudaStream_t)stream, a, (__nv_bfloat16*)ctx, ldo, stats);
   }
   FIRA_CHECK_LAUNCH("fira_attn_fwd");
   return FIRA_OK;
@@ -382,11 +384,11 @@ int attn_bwd_impl(const void* q, long ldq, const void* k, long ldk, const void* 
   const size_t smem = bwd_smem(Lq, Lk);
   if (dtype == FIRA_F32) {
     if ((rc = set_smem(attn_bwd_kernel<float>, smem, "attn_bwd"))) return rc;
-    attn_bwd_kernel<float><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(
+    launch_k(attn_bwd_kernel<float>, dim3(B * H), dim3(NTHR), smem, (cudaStream_t)stream, 
         a, (const float*)ctx, (const float*)d_ctx, ldo, stats, (float*)dq, lddq, (float*)dk, lddk, (float*)dv, lddv);
   } else {
     if ((rc = set_smem(attn_bwd_kernel<__nv_bfloat16>, smem, "attn_bwd"))) return rc;
-    attn_bwd_kernel<__nv_bfloat16><<<B * H, NTHR, smem, (cudaStream_t)stream>>>(
+    launch_k(attn_bwd_kernel<__nv_bfloat16>, dim3(B * H), dim3(NTHR), smem, (cudaStream_t)stream, 
         a, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)d_ctx, ldo, stats, (__nv_bfloat16*)dq, lddq,
         (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv);
   }

@@ -165,9 +165,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     mbar_init_fence();
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    make_chunks(ch, a.ranges, b, a.Lk);
   }
   if (warp == 4) tmem_alloc(smem_addr(&tmem_slot), 512);
+  pdl_wait(); pdl_trigger();       // PDL: the prologue above overlapped the previous kernel's tail (common.cuh)
+  if (threadIdx.x == 0) make_chunks(ch, a.ranges, b, a.Lk);
   for (int i = threadIdx.x; i < MAX_CH * KC; i += THREADS)
     s_mask[i] = i < a.Lk ? (a.key_mask ? a.key_mask[(long)b * a.Lk + i] : (unsigned char)1) : (unsigned char)0;
   tc_fence_before();
@@ -335,7 +336,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int b = blockIdx.x >> 1, g = blockIdx.x & 1;
 
   if (threadIdx.x == 0) {
-    make_chunks(ch, a.ranges, b, a.Lk);
     rm.nch = 0;
     mbar_init(smem_addr(&kv_full), 1);
     mbar_init(smem_addr(&s_full), 1);
@@ -347,6 +347,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     tma_prefetch_desc(&tmV);
   }
   if (warp == 4) tmem_alloc(smem_addr(&tmem_slot), 512);
+  pdl_wait(); pdl_trigger();       // PDL: the prologue above overlapped the previous kernel's tail (common.cuh)
+  if (threadIdx.x == 0) make_chunks(ch, a.ranges, b, a.Lk);
   for (int i = threadIdx.x; i < MAX_CH * KC; i += THREADS)
     s_mask[i] = i < a.Lk ? (a.key_mask ? a.key_mask[(long)b * a.Lk + i] : (unsigned char)1) : (unsigned char)0;
   tc_fence_before();
@@ -559,7 +561,7 @@ int fira_attn_tc_fwd(const void* q, long ldq, const void* k, long ldk, const voi
   const size_t smem = (1 + MAX_CH + 2) * (size_t)TILE + 1024;
   cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "attn_tc_fwd attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
-  attn_tc_fwd_kernel<<<B * 2, THREADS, smem, (cudaStream_t)stream>>>(tk, tv, a);
+  launch_k(attn_tc_fwd_kernel, dim3(B * 2), dim3(THREADS), smem, (cudaStream_t)stream, tk, tv, a);
   FIRA_CHECK_LAUNCH("fira_attn_fwd (tcgen05)");
   return FIRA_OK;
 }
@@ -581,7 +583,7 @@ int fira_attn_tc_bwd(const void* q, long ldq, const void* k, long ldk, const voi
   const size_t smem = 6 * (size_t)TILE + 1024;
   cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "attn_tc_bwd attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
-  attn_tc_bwd_kernel<<<B * 2, THREADS, smem, (cudaStream_t)stream>>>(tk, tv, a);
+  launch_k(attn_tc_bwd_kernel, dim3(B * 2), dim3(THREADS), smem, (cudaStream_t)stream, tk, tv, a);
   FIRA_CHECK_LAUNCH("fira_attn_bwd (tcgen05)");
   return FIRA_OK;
 }

@@ -37,7 +37,35 @@ void fira_set_error(int code, const char* fmt, ...);
 
 static inline bool fira_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// launch mode of every kernel of the library (api.cu; fira_set_pdl / FIRA_PDL): 1 = programmatic dependent launch
+int fira_pdl_on();
+
 #ifdef __CUDACC__
+
+// ---- programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_wait() -- before its first
+//      global-memory access -- and pdl_trigger(): launched with the programmatic-serialization attribute (launch_k
+//      below), its CTAs are scheduled while the previous kernel of the stream drains, run their on-chip prologue
+//      (barrier init, TMEM allocation, tensor-map prefetch), and block in griddepcontrol.wait until that kernel has
+//      completed and flushed.  Because EVERY kernel waits before touching memory, completion is transitive along the
+//      stream.  Inside a captured CUDA graph the attribute becomes a programmatic edge; after a non-kernel node or a
+//      cross-stream join it degrades to a full dependency.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = fira_pdl_on() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr int kWarp = 32;
 constexpr float kLnEps = 1e-5f;

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait(); pdl_trigger();       // PDL: the prologue above overlapped the previous kernel's tail (common.cuh)
 
   if (warp == WARP_MMA) {
     if (lane == 0 && ntiles > 0) {
@@ -417,6 +418,7 @@ __device__ __forceinline__ void seg_unrow(const Segs& s, long r, int& b, int& i)
 }
 
 __global__ void rows_count_kernel(const int* __restrict__ rowptr, Segs s, int N, int* __restrict__ counts) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)s.B * N;
   for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long)gridDim.x * blockDim.x) {
     int b, i; seg_unrow(s, r, b, i);
@@ -427,6 +429,7 @@ __global__ void rows_count_kernel(const int* __restrict__ rowptr, Segs s, int N,
 
 // one 1024-thread CTA: exclusive scan of counts[0..n) -> out[0..n]
 __global__ void rows_scan_kernel(const int* __restrict__ counts, int* __restrict__ out, long n) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   __shared__ int warp_tot[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -459,6 +462,7 @@ __global__ void rows_scan_kernel(const int* __restrict__ counts, int* __restrict
 __global__ void rows_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
                                  Segs s, int N, const int* __restrict__ rowptr_g, int* __restrict__ col_g,
                                  float* __restrict__ val_g) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)s.B * N;
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += (long)gridDim.x * (blockDim.x >> 5)) {
@@ -478,8 +482,8 @@ int launch_fused(int mode, const CUtensorMap& tm, const Params& p, cudaStream_t 
   if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gcn_layer attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   long want = (p.R + 31) / 32;
   const int grid = (int)(want < 148 ? (want < 1 ? 1 : want) : 148);
-  if (mode == 0) gcn_fused_kernel<0><<<grid, THREADS, smem, st>>>(tm, p);
-  else gcn_fused_kernel<1><<<grid, THREADS, smem, st>>>(tm, p);
+  if (mode == 0) launch_k(gcn_fused_kernel<0>, dim3(grid), dim3(THREADS), smem, st, tm, p);
+  else launch_k(gcn_fused_kernel<1>, dim3(grid), dim3(THREADS), smem, st, tm, p);
   return FIRA_OK;
 }
 
@@ -496,10 +500,10 @@ int fira_csr_to_rows(const int* rowptr, const int* col, const float* val, int B,
   const long R = (long)B * N;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (int)((R + 255) / 256 < 148 * 4 ? (R + 255) / 256 : 148 * 4);
-  rows_count_kernel<<<grid, 256, 0, st>>>(rowptr, s, N, counts);
-  rows_scan_kernel<<<1, 1024, 0, st>>>(counts, rowptr_rows, R);
+  launch_k(rows_count_kernel, dim3(grid), dim3(256), 0, st, rowptr, s, N, counts);
+  launch_k(rows_scan_kernel, dim3(1), dim3(1024), 0, st, counts, rowptr_rows, R);
   grid = (int)((R + 7) / 8 < 148 * 8 ? (R + 7) / 8 : 148 * 8);
-  rows_fill_kernel<<<grid, 256, 0, st>>>(rowptr, col, val, s, N, rowptr_rows, col_rows, val_rows);
+  launch_k(rows_fill_kernel, dim3(grid), dim3(256), 0, st, rowptr, col, val, s, N, rowptr_rows, col_rows, val_rows);
   FIRA_CHECK_LAUNCH("fira_csr_to_rows");
   return FIRA_OK;
 }

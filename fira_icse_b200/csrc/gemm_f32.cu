@@ -88,6 +88,7 @@ struct TileLoader {
 // (strip s covers rows ty*4 + s*(BM/(TM/4)) .. so a warp's smem reads are contiguous float4s).
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NTHREADS) gemm_f32_kernel(GemmParams p) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   static_assert((BM / TM) * (BN / TN) == NTHREADS, "thread grid");
   constexpr int SM_ = TM / 4, SN_ = TN / 4;           // strips per thread
   constexpr int MSTRIDE = BM / SM_, NSTRIDE = BN / SN_;
@@ -222,10 +223,10 @@ extern "C" int fira_gemm_f32(const float* A, long lda, int a_kcontig, const floa
   const long big_tiles = (long)((M + 127) / 128) * ((N + 127) / 128) * splits;
   if (big_tiles >= 120) {
     dim3 grid((N + 127) / 128, (M + 127) / 128, splits);
-    gemm_f32_kernel<128, 128, 8, 8><<<grid, NTHREADS, 0, st>>>(p);
+    launch_k(gemm_f32_kernel<128, 128, 8, 8>, dim3(grid), dim3(NTHREADS), 0, st, p);
   } else {
     dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-    gemm_f32_kernel<64, 64, 4, 4><<<grid, NTHREADS, 0, st>>>(p);
+    launch_k(gemm_f32_kernel<64, 64, 4, 4>, dim3(grid), dim3(NTHREADS), 0, st, p);
   }
   FIRA_CHECK_LAUNCH("fira_gemm_f32");
   return FIRA_OK;

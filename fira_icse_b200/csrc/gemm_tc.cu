@@ -114,6 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
+  pdl_wait(); pdl_trigger();       // PDL: the prologue above overlapped the previous kernel's tail (common.cuh)
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -331,7 +332,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, 
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
-  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(NUM_THREADS), smem, st, ta, tb, p);
   return FIRA_OK;
 }
 

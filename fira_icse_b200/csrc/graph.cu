@@ -43,6 +43,7 @@ template <> __device__ __forceinline__ bool edge_nonzero<__nv_bfloat16>(__nv_bfl
 template <typename E>
 __global__ void dense_count_kernel(const E* __restrict__ a, long sb, long si, long sj, int B, int N,
                                    int* __restrict__ counts) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long rows = (long)B * N;
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
@@ -57,6 +58,7 @@ __global__ void dense_count_kernel(const E* __restrict__ a, long sb, long si, lo
 
 // exclusive scan of n counts into rowptr[0..n] by ONE 1024-thread CTA (n = B*650 <= a few 100k)
 __global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ rowptr, long n) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   __shared__ int warp_tot[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -90,6 +92,7 @@ __global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ ro
 template <typename E>
 __global__ void dense_fill_kernel(const E* __restrict__ a, long sb, long si, long sj, int B, int N,
                                   const int* __restrict__ rowptr, int* __restrict__ col, float* __restrict__ val) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long rows = (long)B * N;
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
@@ -112,6 +115,7 @@ __global__ void dense_fill_kernel(const E* __restrict__ a, long sb, long si, lon
 
 __global__ void csr_rowsum_kernel(const int* __restrict__ rowptr, const float* __restrict__ val, Segs s, int N,
                                   float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)s.B * N;
   for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long)gridDim.x * blockDim.x) {
     int b, i; seg_unrow(s, r, b, i);
@@ -132,6 +136,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) csr_spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                        const float* __restrict__ val, const T* __restrict__ x,
                                                        const T* __restrict__ addend, T* __restrict__ y, Segs s, int N) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)s.B * N;
   const int lane = threadIdx.x & 31;
   const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -187,6 +192,7 @@ __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restric
                                                             const float* __restrict__ val, const T* __restrict__ x,
                                                             const T* __restrict__ addend, T* __restrict__ y, Segs s,
                                                             int N) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   constexpr int F = D / LPR;                      // features per lane (16 or 32)
   constexpr int RPW = 32 / LPR;                   // rows per warp
   const long R = (long)s.B * N;
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(256) csr_spmm_pipe_kernel(const int* __restric
                                                             const float* __restrict__ val, const T* __restrict__ x,
                                                             const T* __restrict__ addend, T* __restrict__ y, Segs s,
                                                             int N) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   constexpr int F = D / LPR;
   constexpr int RPW = 32 / LPR;
   const long R = (long)s.B * N;
@@ -349,6 +356,7 @@ __global__ void __launch_bounds__(WARPS * 32) csr_spmm_bulk_kernel(const int* __
                                                                    const T* __restrict__ x,
                                                                    const T* __restrict__ addend, T* __restrict__ y,
                                                                    Segs s, int N) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[WARPS];
   constexpr uint32_t ROW_BYTES = D * sizeof(T);
@@ -447,12 +455,12 @@ int fira_csr_count_dense(const void* edge, int edge_dtype, long stride_b, long s
   cudaStream_t st = (cudaStream_t)stream;
   const long rows = (long)B * N;
   int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-  if (edge_dtype == 0) dense_count_kernel<float><<<grid, 256, 0, st>>>((const float*)edge, stride_b, stride_i, stride_j, B, N, counts);
-  else if (edge_dtype == 2) dense_count_kernel<double><<<grid, 256, 0, st>>>((const double*)edge, stride_b, stride_i, stride_j, B, N, counts);
-  else if (edge_dtype == 1) dense_count_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)edge, stride_b, stride_i, stride_j, B, N, counts);
+  if (edge_dtype == 0) launch_k(dense_count_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)edge, stride_b, stride_i, stride_j, B, N, counts);
+  else if (edge_dtype == 2) launch_k(dense_count_kernel<double>, dim3(grid), dim3(256), 0, st, (const double*)edge, stride_b, stride_i, stride_j, B, N, counts);
+  else if (edge_dtype == 1) launch_k(dense_count_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)edge, stride_b, stride_i, stride_j, B, N, counts);
   else { fira_set_error(FIRA_ERR_DTYPE, "csr_count_dense: edge dtype %d", edge_dtype); return FIRA_ERR_DTYPE; }
   FIRA_CHECK_LAUNCH("fira_csr_count_dense");
-  scan_kernel<<<1, 1024, 0, st>>>(counts, rowptr, rows);
+  launch_k(scan_kernel, dim3(1), dim3(1024), 0, st, counts, rowptr, rows);
   FIRA_CHECK_LAUNCH("fira_csr_count_dense/scan");
   return FIRA_OK;
 }
@@ -462,9 +470,9 @@ int fira_csr_fill_dense(const void* edge, int edge_dtype, long stride_b, long st
   cudaStream_t st = (cudaStream_t)stream;
   const long rows = (long)B * N;
   int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-  if (edge_dtype == 0) dense_fill_kernel<float><<<grid, 256, 0, st>>>((const float*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
-  else if (edge_dtype == 2) dense_fill_kernel<double><<<grid, 256, 0, st>>>((const double*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
-  else if (edge_dtype == 1) dense_fill_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
+  if (edge_dtype == 0) launch_k(dense_fill_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
+  else if (edge_dtype == 2) launch_k(dense_fill_kernel<double>, dim3(grid), dim3(256), 0, st, (const double*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
+  else if (edge_dtype == 1) launch_k(dense_fill_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)edge, stride_b, stride_i, stride_j, B, N, rowptr, col, val);
   else { fira_set_error(FIRA_ERR_DTYPE, "csr_fill_dense: edge dtype %d", edge_dtype); return FIRA_ERR_DTYPE; }
   FIRA_CHECK_LAUNCH("fira_csr_fill_dense");
   return FIRA_OK;
@@ -476,7 +484,7 @@ int fira_csr_rowsum(const int* rowptr, const float* val, int B, int n_code, int 
   const int N = n_code + n_sub + n_ast;
   FIRA_CHECK_ARG(n_code > 0 && n_sub >= 0 && n_ast >= 0, FIRA_ERR_SHAPE, "csr_rowsum: segments");
   const long R = (long)B * N;
-  csr_rowsum_kernel<<<(int)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, val, s, N, out);
+  launch_k(csr_rowsum_kernel, dim3((int)((R + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, rowptr, val, s, N, out);
   FIRA_CHECK_LAUNCH("fira_csr_rowsum");
   return FIRA_OK;
 }
@@ -499,13 +507,13 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     long ctas = (R + 7) / 8;
     const long cap = 148L * 8 * 4;
     int grid = (int)(ctas < cap ? ctas : cap);
-    DISPATCH_T(dtype, csr_spmm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, val, (const T*)x,
+    DISPATCH_T(dtype, launch_k(csr_spmm_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, rowptr, col, val, (const T*)x,
                                                                                    (const T*)addend, (T*)y, s, N);)
   } else if (variant == 4) {
     long ctas = (R + 15) / 16;               // 8 warps x 2 rows
     const long cap = 148L * 8 * 4;
     int grid = (int)(ctas < cap ? ctas : cap);
-    DISPATCH_T(dtype, csr_spmm_part_kernel<T, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, launch_k(csr_spmm_part_kernel<T, 16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else if (variant == 6) {                 // persistent one-wave grid, metadata pipelined two rows ahead (unmeasured)
     const int rows_per_cta = dtype == FIRA_BF16 ? 16 : 8;
@@ -513,10 +521,10 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     const long cap = 148L * 4;               // 64 registers/thread -> 4 CTAs of 256 threads per SM
     int grid = (int)(ctas < cap ? ctas : cap);
     if (dtype == FIRA_BF16) {
-      csr_spmm_pipe_kernel<__nv_bfloat16, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      launch_k(csr_spmm_pipe_kernel<__nv_bfloat16, 16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
           rowptr, col, val, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)y, s, N);
     } else {
-      csr_spmm_pipe_kernel<float, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      launch_k(csr_spmm_pipe_kernel<float, 32>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
           rowptr, col, val, (const float*)x, (const float*)addend, (float*)y, s, N);
     }
   } else if (variant == 3) {
@@ -533,7 +541,7 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     long ctas = (R + (long)GR * WARPS - 1) / ((long)GR * WARPS);
     const long cap = 148L * 8;
     int grid = (int)(ctas < cap ? ctas : cap);
-    DISPATCH_T(dtype, csr_spmm_bulk_kernel<T, WARPS><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, launch_k(csr_spmm_bulk_kernel<T, WARPS>, dim3(grid), dim3(WARPS * 32), smem, (cudaStream_t)stream, 
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
   } else {
     fira_set_error(FIRA_ERR_ARG, "gcn_aggregate: unknown FIRA_SPMM_VARIANT %d (1, 3, 4, 6)", variant);

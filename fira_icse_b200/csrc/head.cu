@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restric
                                                               const unsigned char* __restrict__ row_mask,
                                                               const int* __restrict__ ranges,
                                                               float* __restrict__ sc, int B, int Tn, int S) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   // src_mask / row_mask (optional): padded source positions are overwritten with -1e9 by the mixture kernel
   // (Model.py:61) and target rows without a label never reach the loss -- both are skipped (score 0 written).
   const float b_res = *b_res_p;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) copy_scores_bwd_kernel(const T* __restric
                                                               T* __restrict__ d_src, float* __restrict__ d_tgt,
                                                               float* __restrict__ d_w, float* __restrict__ d_b, int B,
                                                               int Tn, int S) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   extern __shared__ __align__(16) float dyn_smem[];
   float (*tg)[D] = reinterpret_cast<float (*)[D]>(dyn_smem);                    // [TMAX][D]
   float (*dtg)[D] = reinterpret_cast<float (*)[D]>(dyn_smem + TMAX * D);        // [TMAX][D]
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ log
                                                        const int* __restrict__ label, float* __restrict__ stats,
                                                        float* __restrict__ nll, int* __restrict__ argmax_out, int Tn,
                                                        int V, int S) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   __shared__ MaxSum sh_ms[8];
   __shared__ ArgMax sh_am[8];
   __shared__ float bc[8];
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ log
                                                        const float* __restrict__ upstream, T* __restrict__ d_logits,
                                                        float* __restrict__ d_sc, float* __restrict__ d_gate_logit,
                                                        unsigned char* __restrict__ row_active, int Tn, int V, int S) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long row = blockIdx.x;
   const int b = (int)(row / Tn);
   const float* st = stats + row * 8;
@@ -335,7 +339,7 @@ static int copy_scores_fwd_impl(const void* src_proj, const void* tgt_proj, cons
   FIRA_CHECK_ARG(T_len > 0 && T_len <= TMAX, FIRA_ERR_SHAPE, "copy_scores_fwd: T_len %d > %d", T_len, TMAX);
   if (B == 0 || S == 0) return FIRA_OK;
   dim3 grid((S + 31) / 32, B);
-  DISPATCH_T(dtype, copy_scores_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(copy_scores_fwd_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)src_proj, (const T*)tgt_proj, w_res, b_res, src_mask, row_mask, ranges, scores, B, T_len, S);)
   FIRA_CHECK_LAUNCH("fira_copy_scores_fwd");
   return FIRA_OK;
@@ -353,7 +357,7 @@ static int copy_scores_bwd_impl(const void* src_proj, const void* tgt_proj, cons
       ? cudaFuncSetAttribute(copy_scores_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
       : cudaFuncSetAttribute(copy_scores_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "copy_scores_bwd attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
-  DISPATCH_T(dtype, copy_scores_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(copy_scores_bwd_kernel<T>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 
       (const T*)src_proj, (const T*)tgt_proj, w_res, d_scores, row_active, ranges, (T*)d_src_proj, d_tgt_proj, d_w_res,
       d_b_res, B, T_len, S);)
   FIRA_CHECK_LAUNCH("fira_copy_scores_bwd");
@@ -395,7 +399,7 @@ int fira_pointer_mix_nll_fwd(const void* logits, long ld_logits, const float* co
                              int* argmax_out, long rows, int T_len, int V, int S, int dtype, void* stream) {
   FIRA_CHECK_ARG(rows >= 0 && T_len > 0 && V > 0 && S > 0, FIRA_ERR_SHAPE, "pointer_mix_nll_fwd: shape");
   if (rows == 0) return FIRA_OK;
-  DISPATCH_T(dtype, head_fwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(head_fwd_kernel<T>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)logits, ld_logits, copy_scores, gate_logits, mem_mask, label, stats, nll, argmax_out, T_len, V, S);)
   FIRA_CHECK_LAUNCH("fira_pointer_mix_nll_fwd");
   return FIRA_OK;
@@ -407,7 +411,7 @@ int fira_pointer_mix_nll_bwd(const void* logits, long ld_logits, const float* co
                              unsigned char* row_active, long rows, int T_len, int V, int S, int dtype, void* stream) {
   FIRA_CHECK_ARG(rows >= 0 && T_len > 0 && V > 0 && S > 0, FIRA_ERR_SHAPE, "pointer_mix_nll_bwd: shape");
   if (rows == 0) return FIRA_OK;
-  DISPATCH_T(dtype, head_bwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(head_bwd_kernel<T>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, 
       (const T*)logits, ld_logits, copy_scores, mem_mask, label, stats, upstream, (T*)d_logits, d_copy_scores,
       d_gate_logits, row_active, T_len, V, S);)
   FIRA_CHECK_LAUNCH("fira_pointer_mix_nll_bwd");

@@ -30,6 +30,7 @@ __global__ void embed_nodes_kernel(const int* __restrict__ sou, const int* __res
                                    const float* __restrict__ pe, const int* __restrict__ pos_idx,
                                    T* __restrict__ out_code, T* __restrict__ out_rest, int B, int n_code, int n_sub,
                                    int n_ast) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)B * (n_code + n_sub + n_ast);
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < R; r += (long)gridDim.x * ROWS_PER_CTA) {
@@ -61,6 +62,7 @@ __global__ void embed_nodes_bwd_kernel(const int* __restrict__ sou, const int* _
                                        const int* __restrict__ ast, const T* __restrict__ d_code,
                                        const T* __restrict__ d_rest, float* __restrict__ d_emb,
                                        float* __restrict__ d_ast_emb, int B, int n_code, int n_sub, int n_ast) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)B * (n_code + n_sub + n_ast);
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < R; r += (long)gridDim.x * ROWS_PER_CTA) {
@@ -81,6 +83,7 @@ __global__ void embed_nodes_bwd_kernel(const int* __restrict__ sou, const int* _
 template <typename T>
 __global__ void embed_rows_kernel(const int* __restrict__ ids, const float* __restrict__ emb,
                                   const float* __restrict__ pe, T* __restrict__ out, long rows, int period) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * ROWS_PER_CTA) {
     float v[8], q[8];
@@ -94,10 +97,17 @@ __global__ void embed_rows_kernel(const int* __restrict__ ids, const float* __re
 template <typename T>
 __global__ void embed_rows_bwd_kernel(const int* __restrict__ ids, const T* __restrict__ g, float* __restrict__ d_emb,
                                       long rows) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const int lane = threadIdx.x & 31;
   for (long r = (long)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * ROWS_PER_CTA) {
     float v[8];
     Act<T>::load8(g + r * D + lane * 8, v);
+    // rows whose gradient is exactly zero (padded target positions: no loss, masked as keys) add nothing; skipping
+    // them avoids ~1,000 rows of atomics serialising on the <pad> row of the table (measured 105 us -> a few us)
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nz |= v[i] != 0.f;
+    if (!__any_sync(0xffffffffu, nz)) continue;
     float* o = d_emb + (long)ids[r] * D + lane * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) atomicAdd(o + i, v[i]);
@@ -112,6 +122,7 @@ __global__ void ln_fwd_kernel(const T* __restrict__ z, const T* __restrict__ res
                               const float* __restrict__ beta, T* __restrict__ outA, T* __restrict__ outB, long split,
                               float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, float p_drop,
                               uint64_t seed, const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
   const int lane = threadIdx.x & 31;
   float g[8], bt[8];
@@ -153,6 +164,7 @@ __global__ void ln_bwd_kernel(const T* __restrict__ doutA, const T* __restrict__
                               T* __restrict__ d_resid, int d_resid_accum, float* __restrict__ d_gamma,
                               float* __restrict__ d_beta, long rows, float p_drop, uint64_t seed,
                               const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
   __shared__ float red[2][ROWS_PER_CTA][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -222,6 +234,7 @@ __global__ void comb_gate_fwd_kernel(const T* __restrict__ qk, long ld_qk, const
                                      const int* __restrict__ mark, T* __restrict__ out, long rows, float scale,
                                      float p_drop, uint64_t seed, const uint64_t* __restrict__ seed_ctr,
                                      uint32_t stream_id) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
   const int lane = threadIdx.x & 31;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -248,6 +261,7 @@ __global__ void comb_gate_bwd_kernel(const T* __restrict__ qk, long ld_qk, const
                                      const int* __restrict__ mark, const T* __restrict__ d_out, T* __restrict__ d_qk,
                                      float* __restrict__ d_vtab, long rows, float scale, float p_drop, uint64_t seed,
                                      const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
   __shared__ float red[ROWS_PER_CTA][4][D + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -302,6 +316,7 @@ template <typename T>
 __global__ void comb_gate3_fwd_kernel(const T* __restrict__ qp, const T* __restrict__ kp, const T* __restrict__ vp,
                                       T* __restrict__ out, long rows, float scale, float p_drop, uint64_t seed,
                                       const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
   const int lane = threadIdx.x & 31;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -328,6 +343,7 @@ __global__ void comb_gate3_bwd_kernel(const T* __restrict__ qp, const T* __restr
                                       const T* __restrict__ d_out, T* __restrict__ dqp, T* __restrict__ dkp,
                                       T* __restrict__ dvp, long rows, float scale, float p_drop, uint64_t seed,
                                       const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
   const int lane = threadIdx.x & 31;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -361,6 +377,7 @@ __global__ void comb_gate3_bwd_kernel(const T* __restrict__ qp, const T* __restr
 template <typename T>
 __global__ void zero_pad_rows_kernel(T* __restrict__ x, long ld, int width, const int* __restrict__ off, int B, int Rc,
                                      int Rs) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const int lo0 = off[B], lo1 = Rc + off[(B + 1) + B];
   const long n0 = Rc - lo0, n1 = (long)Rc + Rs - lo1;
   const int vec = width / 8;
@@ -376,6 +393,7 @@ __global__ void zero_pad_rows_kernel(T* __restrict__ x, long ld, int width, cons
 // out[n] += sum_m x[m, n]; one warp covers 32 columns x a strided set of rows.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long ld, long M, int N, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int wy = threadIdx.x >> 5;
@@ -396,6 +414,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, long ld, long M, int N, f
 template <typename T>
 __global__ void colsum_weighted_kernel(const T* __restrict__ x, long ld, const float* __restrict__ w, long M, int N,
                                        float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int wy = threadIdx.x >> 5;
@@ -419,6 +438,7 @@ __global__ void colsum_weighted_kernel(const T* __restrict__ x, long ld, const f
 template <typename T>
 __global__ void pack_memory_kernel(const T* __restrict__ code, const T* __restrict__ rest, T* __restrict__ mem, int B,
                                    int n_code, int n_sub) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const int S = n_code + n_sub;
   const long rows = (long)B * S;
   const int lane = threadIdx.x & 31;
@@ -434,6 +454,7 @@ __global__ void pack_memory_kernel(const T* __restrict__ code, const T* __restri
 template <typename T>
 __global__ void unpack_memory_kernel(const T* __restrict__ d_mem, T* __restrict__ d_code, T* __restrict__ d_rest, int B,
                                      int n_code, int n_sub, int n_ast) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   const long R = (long)B * (n_code + n_sub + n_ast);
   const int S = n_code + n_sub;
   const int lane = threadIdx.x & 31;
@@ -460,6 +481,7 @@ __global__ void unpack_memory_kernel(const T* __restrict__ d_mem, T* __restrict_
 // d = (h > 0) ? d : 0, 8 elements per thread (n % 8 == 0)
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ h, T* __restrict__ d, long n8) {
+  pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
     float a[8], g[8];
     Act<T>::load8(h + i * 8, a);
@@ -493,7 +515,7 @@ int fira_embed_nodes_pos_fwd(const int* sou, const int* pos, const int* sub_toke
   FIRA_CHECK_ARG(fira_aligned16(out_code) && fira_aligned16(out_rest) && fira_aligned16(emb), FIRA_ERR_ALIGN,
                  "embed_nodes: 16-B alignment");
   const long R = (long)B * (n_code + n_sub + n_ast);
-  DISPATCH_T(dtype, embed_nodes_kernel<T><<<row_grid(R), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(embed_nodes_kernel<T>, dim3(row_grid(R)), dim3(CTA), 0, (cudaStream_t)stream, 
       sou, sub_token, ast_change, emb, ast_emb, pos_table, pos, (T*)out_code, (T*)out_rest, B, n_code, n_sub, n_ast);)
   FIRA_CHECK_LAUNCH("fira_embed_nodes_fwd");
   return FIRA_OK;
@@ -502,7 +524,7 @@ int fira_embed_nodes_pos_fwd(const int* sou, const int* pos, const int* sub_toke
 int fira_zero_pad_rows(void* x, long ld, int width, const int* off, int B, int Rc, int Rs, int dtype, void* stream) {
   FIRA_CHECK_ARG(x && off && B > 0 && width > 0 && width % 8 == 0 && ld >= width, FIRA_ERR_ARG, "zero_pad_rows: arguments");
   FIRA_CHECK_ARG(fira_aligned16(x) && (ld % 8) == 0, FIRA_ERR_ALIGN, "zero_pad_rows: 16-B alignment");
-  DISPATCH_T(dtype, zero_pad_rows_kernel<T><<<148, 256, 0, (cudaStream_t)stream>>>((T*)x, ld, width, off, B, Rc, Rs);)
+  DISPATCH_T(dtype, launch_k(zero_pad_rows_kernel<T>, dim3(148), dim3(256), 0, (cudaStream_t)stream, (T*)x, ld, width, off, B, Rc, Rs);)
   FIRA_CHECK_LAUNCH("fira_zero_pad_rows");
   return FIRA_OK;
 }
@@ -512,7 +534,7 @@ int fira_embed_nodes_bwd(const int* sou, const int* sub_token, const int* ast_ch
                          int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "embed_nodes_bwd: dim %d != 256", dim);
   const long R = (long)B * (n_code + n_sub + n_ast);
-  DISPATCH_T(dtype, embed_nodes_bwd_kernel<T><<<row_grid(R), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(embed_nodes_bwd_kernel<T>, dim3(row_grid(R)), dim3(CTA), 0, (cudaStream_t)stream, 
       sou, sub_token, ast_change, (const T*)d_code, (const T*)d_rest, d_emb, d_ast_emb, B, n_code, n_sub, n_ast);)
   FIRA_CHECK_LAUNCH("fira_embed_nodes_bwd");
   return FIRA_OK;
@@ -522,7 +544,7 @@ int fira_embed_rows_fwd(const int* ids, const float* emb, const float* pos_table
                         int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "embed_rows: dim %d != 256", dim);
   FIRA_CHECK_ARG(period > 0, FIRA_ERR_SHAPE, "embed_rows: period");
-  DISPATCH_T(dtype, embed_rows_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(ids, emb, pos_table,
+  DISPATCH_T(dtype, launch_k(embed_rows_kernel<T>, dim3(row_grid(rows)), dim3(CTA), 0, (cudaStream_t)stream, ids, emb, pos_table,
                                                                                          (T*)out, rows, period);)
   FIRA_CHECK_LAUNCH("fira_embed_rows_fwd");
   return FIRA_OK;
@@ -530,7 +552,7 @@ int fira_embed_rows_fwd(const int* ids, const float* emb, const float* pos_table
 
 int fira_embed_rows_bwd(const int* ids, const void* d_out, float* d_emb, long rows, int dim, int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "embed_rows_bwd: dim %d != 256", dim);
-  DISPATCH_T(dtype, embed_rows_bwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(ids, (const T*)d_out,
+  DISPATCH_T(dtype, launch_k(embed_rows_bwd_kernel<T>, dim3(row_grid(rows)), dim3(CTA), 0, (cudaStream_t)stream, ids, (const T*)d_out,
                                                                                              d_emb, rows);)
   FIRA_CHECK_LAUNCH("fira_embed_rows_bwd");
   return FIRA_OK;
@@ -544,7 +566,7 @@ int fira_ln_residual_fwd(const void* z, const void* resid, const float* gamma, c
   FIRA_CHECK_ARG(fira_aligned16(z) && fira_aligned16(resid) && fira_aligned16(outA) && fira_aligned16(outB),
                  FIRA_ERR_ALIGN, "ln_residual_fwd: 16-B alignment");
   if (rows == 0) return FIRA_OK;
-  DISPATCH_T(dtype, ln_fwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(ln_fwd_kernel<T>, dim3(row_grid(rows)), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)z, (const T*)resid, gamma, beta, (T*)outA, (T*)outB, split, mean, rstd, rows, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_ln_residual_fwd");
   return FIRA_OK;
@@ -558,7 +580,7 @@ int fira_ln_residual_bwd(const void* d_outA, const void* d_outB, long split, con
   if (rows == 0) return FIRA_OK;
   long g = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   int grid = (int)(g < 148L * 4 ? g : 148L * 4);   // few CTAs -> few d_gamma/d_beta atomics
-  DISPATCH_T(dtype, ln_bwd_kernel<T><<<grid, CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(ln_bwd_kernel<T>, dim3(grid), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)d_outA, (const T*)d_outB, split, (const T*)z, (const T*)resid, mean, rstd, gamma, (T*)d_z,
       (T*)d_resid, d_resid_accum, d_gamma, d_beta, rows, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_ln_residual_bwd");
@@ -571,7 +593,7 @@ int fira_comb_gate_fwd(const void* qk, long ld_qk, const float* vtab, const int*
   FIRA_CHECK_ARG(ld_qk >= 2 * D && (ld_qk % 8) == 0, FIRA_ERR_SHAPE, "comb_gate_fwd: ld_qk %ld", ld_qk);
   if (rows == 0) return FIRA_OK;
   const float scale = 1.f / sqrtf((float)d_head);
-  DISPATCH_T(dtype, comb_gate_fwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(comb_gate_fwd_kernel<T>, dim3(row_grid(rows)), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)qk, ld_qk, vtab, mark, (T*)out, rows, scale, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate_fwd");
   return FIRA_OK;
@@ -585,7 +607,7 @@ int fira_comb_gate_bwd(const void* qk, long ld_qk, const float* vtab, const int*
   const float scale = 1.f / sqrtf((float)d_head);
   long g = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   int grid = (int)(g < 148L * 4 ? g : 148L * 4);
-  DISPATCH_T(dtype, comb_gate_bwd_kernel<T><<<grid, CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(comb_gate_bwd_kernel<T>, dim3(grid), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)qk, ld_qk, vtab, mark, (const T*)d_out, (T*)d_qk, d_vtab, rows, scale, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate_bwd");
   return FIRA_OK;
@@ -597,7 +619,7 @@ int fira_comb_gate3_fwd(const void* q, const void* k, const void* v, void* out, 
   FIRA_CHECK_ARG(d_head > 0, FIRA_ERR_SHAPE, "comb_gate3_fwd: d_head %d", d_head);
   if (rows == 0) return FIRA_OK;
   const float scale = 1.f / sqrtf((float)d_head);
-  DISPATCH_T(dtype, comb_gate3_fwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(comb_gate3_fwd_kernel<T>, dim3(row_grid(rows)), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)q, (const T*)k, (const T*)v, (T*)out, rows, scale, p_drop, seed, seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate3_fwd");
   return FIRA_OK;
@@ -610,7 +632,7 @@ int fira_comb_gate3_bwd(const void* q, const void* k, const void* v, const void*
   FIRA_CHECK_ARG(d_head > 0, FIRA_ERR_SHAPE, "comb_gate3_bwd: d_head %d", d_head);
   if (rows == 0) return FIRA_OK;
   const float scale = 1.f / sqrtf((float)d_head);
-  DISPATCH_T(dtype, comb_gate3_bwd_kernel<T><<<row_grid(rows), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(comb_gate3_bwd_kernel<T>, dim3(row_grid(rows)), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)q, (const T*)k, (const T*)v, (const T*)d_out, (T*)d_q, (T*)d_k, (T*)d_v, rows, scale, p_drop, seed,
       seed_ctr, stream_id);)
   FIRA_CHECK_LAUNCH("fira_comb_gate3_bwd");
@@ -623,10 +645,10 @@ int fira_colsum(const void* x, long ld, long M, int N, const float* row_weight, 
   if (gy > 64) gy = 64;
   dim3 grid((N + 31) / 32, (unsigned)gy);
   if (row_weight) {
-    DISPATCH_T(dtype, colsum_weighted_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, row_weight,
+    DISPATCH_T(dtype, launch_k(colsum_weighted_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)x, ld, row_weight,
                                                                                          M, N, out);)
   } else {
-    DISPATCH_T(dtype, colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, M, N, out);)
+    DISPATCH_T(dtype, launch_k(colsum_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)x, ld, M, N, out);)
   }
   FIRA_CHECK_LAUNCH("fira_colsum");
   return FIRA_OK;
@@ -637,7 +659,7 @@ int fira_relu_bwd(const void* h, void* d, long n, int dtype, void* stream) {
   if (n == 0) return FIRA_OK;
   long blocks = (n / 8 + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
-  DISPATCH_T(dtype, relu_bwd_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)h, (T*)d, n / 8);)
+  DISPATCH_T(dtype, launch_k(relu_bwd_kernel<T>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)h, (T*)d, n / 8);)
   FIRA_CHECK_LAUNCH("fira_relu_bwd");
   return FIRA_OK;
 }
@@ -645,7 +667,7 @@ int fira_relu_bwd(const void* h, void* d, long n, int dtype, void* stream) {
 int fira_pack_memory(const void* code, const void* rest, void* mem, int B, int n_code, int n_sub, int dim, int dtype,
                      void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "pack_memory: dim %d != 256", dim);
-  DISPATCH_T(dtype, pack_memory_kernel<T><<<row_grid((long)B * (n_code + n_sub)), CTA, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_k(pack_memory_kernel<T>, dim3(row_grid((long)B * (n_code + n_sub))), dim3(CTA), 0, (cudaStream_t)stream, 
       (const T*)code, (const T*)rest, (T*)mem, B, n_code, n_sub);)
   FIRA_CHECK_LAUNCH("fira_pack_memory");
   return FIRA_OK;
@@ -654,8 +676,7 @@ int fira_pack_memory(const void* code, const void* rest, void* mem, int B, int n
 int fira_unpack_memory(const void* d_mem, void* d_code, void* d_rest, int B, int n_code, int n_sub, int n_ast, int dim,
                        int dtype, void* stream) {
   FIRA_CHECK_ARG(dim == D, FIRA_ERR_SHAPE, "unpack_memory: dim %d != 256", dim);
-  DISPATCH_T(dtype, unpack_memory_kernel<T><<<row_grid((long)B * (n_code + n_sub + n_ast)), CTA, 0,
-                                              (cudaStream_t)stream>>>((const T*)d_mem, (T*)d_code, (T*)d_rest, B,
+  DISPATCH_T(dtype, launch_k(unpack_memory_kernel<T>, dim3(row_grid((long)B * (n_code + n_sub + n_ast))), dim3(CTA), 0, (cudaStream_t)stream, (const T*)d_mem, (T*)d_code, (T*)d_rest, B,
                                                                       n_code, n_sub, n_ast);)
   FIRA_CHECK_LAUNCH("fira_unpack_memory");
   return FIRA_OK;

@@ -39,6 +39,12 @@ extern "C" {
 int fira_version(void);                    /* ABI version, bumped on any signature change */
 const char* fira_last_error_string(void);
 int fira_built_arch(void);                 /* 100 when compiled for sm_100a */
+/* Launch mode of every kernel of the library (the one process-wide switch, atomic): on = programmatic dependent
+ * launch -- a kernel's CTAs are scheduled while the previous kernel of the stream drains and block in
+ * griddepcontrol.wait before their first global-memory access (results are identical; launch gaps shrink).
+ * Default: on, FIRA_PDL=0 in the environment turns it off. */
+int fira_set_pdl(int on);
+int fira_get_pdl(void);
 
 /* ---- generic fp32 Linear pieces (every nn.Linear of the path; e.g. gnn_transformer.py:78,82,
  *      141-143,158,171-173,200-204; Model.py:16-19,54).
