@@ -373,6 +373,13 @@ def run_gpu_arm(args):
     from fira_icse_b200.parallel import DataParallelStep
 
     B = PER_GPU_BATCH
+
+    def adam_factory(m):
+        # Adam lr 1e-4 (run_model.py:60,101-109): the library's flat Adam (optim.FlatAdam, one launch per step) unless
+        # FIRA_TORCH_ADAM=1 asks for torch.optim.Adam(fused=True) as the A/B
+        if os.environ.get("FIRA_TORCH_ADAM", "0") != "0":
+            return lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True)
+        return lambda ps: F.FlatAdam(ps, lr=1e-4, groups=m.flat_groups())
     torch.manual_seed(0)
     model = F.TransModel(model_args()).to(dev)
     model.train()
@@ -422,7 +429,7 @@ def run_gpu_arm(args):
     last_loss = [0.0]
     if args.graph:
         # whole step captured in a CUDA graph (fira_icse_b200/engine.py): one cudaGraphLaunch per step
-        eng = GraphedTrainStep(model, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True),
+        eng = GraphedTrainStep(model, B, adam_factory(model),
                                edge_capacity=(max(pb.nnz for pb in pool_host) + 4095) // 4096 * 4096 * 2 if packed else None)
         eng.load(pool_dev[0])
         eng.capture()                                                # one eager step + capture of this shape
@@ -561,7 +568,7 @@ def run_gpu_arm(args):
         m32.load_state_dict(model.state_dict())
         m32.train()
         m32.set_precision("fp32")
-        eng32 = GraphedTrainStep(m32, B, lambda ps: torch.optim.Adam(ps, lr=1e-4, fused=True, capturable=True),
+        eng32 = GraphedTrainStep(m32, B, adam_factory(m32),
                                  edge_capacity=eng.cap)
         for hb in pool_dev:
             eng32.step(hb)
@@ -617,7 +624,7 @@ def run_gpu_arm(args):
                        "precision_mode": ("bf16 throughput (bf16 activations, tcgen05 GEMMs with fp32 TMEM accumulators, "
                                           "fp32 parameters/statistics/gradients)" if args.precision == "bf16" else
                                           "fp32 parity (fp32 storage, fp32 FFMA accumulate)"),
-                       "optimizer": "Adam lr 1e-4 (torch fused), dropout on (0.1 / GCN 0.2)",
+                       "optimizer": ("Adam lr 1e-4 (torch.optim.Adam fused)" if os.environ.get("FIRA_TORCH_ADAM", "0") != "0" else "Adam lr 1e-4 (fira_adam_flat: one launch over the flat parameter buffer)") + ", dropout on (0.1 / GCN 0.2)",
                        "launch": "whole step replayed as one CUDA graph" if args.graph else "eager launches",
                        "padding": ("per-commit packed batches: node rows = the real nodes of every commit (segments padded to "
                                    "1024/512/512-row buckets); loss and gradients equal the padded batch" if packed else

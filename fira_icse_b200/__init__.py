@@ -7,6 +7,7 @@ loudly when libfira_b200.so is missing -- there is no CPU fallback.
 from ._lib import FiraLibraryError, LIB_PATH  # noqa: F401
 from .graph import PackedEdges  # noqa: F401
 from .model import CopyNet, TransModel  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
 from .modules import (Attention, Combination, CombinationLayer, Decoder, Encoder, FeedForward, GCN,  # noqa: F401
                       position_encoding)
 

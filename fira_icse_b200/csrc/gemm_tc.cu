@@ -15,6 +15,7 @@
 // splits > 1: split-K across blockIdx.z, fp32 partials atomically added into a zero-filled C.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <atomic>
 #include "common.cuh"
 #include "fira_b200.h"
 
@@ -32,7 +33,18 @@ struct TcParams {
   int relu; int accumulate;
   int splits; int kblocks_per_split;
   int a_kmajor, b_kmajor;
+  unsigned long long* probe;   // debugging aid (fira_debug_set_probe): CTA (0,0,0) stamps %globaltimer at its phase boundaries
 };
+
+std::atomic<unsigned long long*> g_probe{nullptr};
+
+__device__ __forceinline__ void stamp(const TcParams& p, int slot) {
+  if (p.probe && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.probe[slot] = t;
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,6 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_begin = blockIdx.z * p.kblocks_per_split;
   const int kb_end = min(kb_total, kb_begin + p.kblocks_per_split);
   const int nkb = kb_end - kb_begin;
+  if (threadIdx.x == 0) stamp(p, 0);                 // kernel entry
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_addr(&full_bar[s]), 1); mbar_init(smem_addr(&empty_bar[s]), 1); }
@@ -114,7 +127,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
+  if (threadIdx.x == 0) stamp(p, 1);                 // prologue done (barriers, TMEM)
   pdl_wait(); pdl_trigger();       // PDL: the prologue above overlapped the previous kernel's tail (common.cuh)
+  if (threadIdx.x == 0) stamp(p, 2);                 // previous kernel complete
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -139,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n0 + j * 64, k0, fb);
       }
     }
+    stamp(p, 3);                                     // every TMA load issued
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
@@ -150,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(smem_addr(&full_bar[s]), ph);
       tc_fence_after();
+      if (i == 0) stamp(p, 4);                       // first operand stage landed
       const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -161,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(smem_addr(&empty_bar[s]));        // frees the stage when these MMAs have read it
     }
     umma_commit(smem_addr(&tmem_full_bar));         // accumulator complete
+    stamp(p, 5);                                     // every MMA issued
   } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> registers -> smem (lane = row) -> global (lane = column) =====
     // tcgen05.ld hands every lane ONE accumulator row; storing that straight to global makes each warp
@@ -181,6 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_addr(&tmem_full_bar), 0);
       tc_fence_after();
     }
+    if (warp == 2 && lane == 0) stamp(p, 6);         // accumulator visible to the epilogue
     const bool first = blockIdx.z == 0;
     const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1
@@ -288,12 +307,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();                                 // staging block free for the next column pass
     }
   }
+  if (warp == 2 && lane == 0) stamp(p, 7);           // this warp's stores issued
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(BN));
   }
+  if (threadIdx.x == 0) stamp(p, 8);                 // exit
 }
 
 // ---------------------------------------------------------------- host side
@@ -350,6 +371,14 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cuda
 
 }  // namespace
 
+// debugging aid: `probe` = device buffer of >= 16 uint64 (or NULL to switch off); the next fira_gemm_bf16_tc launches make
+// CTA (0,0,0) write %globaltimer at: 0 entry, 1 prologue done, 2 previous kernel complete (PDL wait), 3 TMA loads issued,
+// 4 first stage landed, 5 MMAs issued, 6 accumulator visible to the epilogue, 7 epilogue stores issued, 8 exit
+extern "C" int fira_debug_set_probe(void* probe) {
+  g_probe.store((unsigned long long*)probe, std::memory_order_relaxed);
+  return FIRA_OK;
+}
+
 extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
                                  long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
                                  const float* rc, int relu, int accumulate, int splits, void* stream) {
@@ -382,7 +411,8 @@ extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const vo
   if (splits > kb_total) splits = kb_total;
   int per = (kb_total + splits - 1) / splits;
   splits = (kb_total + per - 1) / per;
-  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits, per, a_kmajor, b_kmajor};
+  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits, per, a_kmajor, b_kmajor,
+             g_probe.load(std::memory_order_relaxed)};
   if (splits > 1 && !accumulate) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
     if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_bf16_tc memset: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }

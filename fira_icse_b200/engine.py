@@ -26,7 +26,9 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import optim as _optim
 from .graph import PackedEdges
+from .optim import FlatAdam
 from .packed import PackedBatch
 from .parallel import FlatGradBucket
 
@@ -105,14 +107,19 @@ class GraphedTrainStep:
         self.opt_factory = optimizer_factory
         self.opt_pair = None
         self.opt_stream = None
-        self.opt_overlap = self.world == 1 and not self.split and os.environ.get("FIRA_OPT_OVERLAP", "0") != "0"
+        self.opt_overlap = self.world == 1 and not self.split and os.environ.get("FIRA_OPT_OVERLAP", "1") != "0"
         self.dev = next(model.parameters()).device
         self.cap = edge_capacity or batch_size * 4096
         self.n_global = torch.ones(1, dtype=torch.float32, device=self.dev)     # global token count (all ranks)
         self.seed_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
         model.encoder.seed_ctr = model.decoder.seed_ctr = self.seed_ctr
         self.bucket = FlatGradBucket(model.live_parameters())
-        self.optimizer = optimizer_factory(self.bucket.params)
+        # the overlapped modes train with TWO optimizers (head/decoder parameters | encoder parameters) found by the
+        # first split backward; the single optimizer of the other modes is built right away
+        self.two_opts = self.opt_overlap or (self.split and os.environ.get("FIRA_DP_TWO_OPTS", "1") != "0")
+        self.optimizer = None if self.two_opts else optimizer_factory(self.bucket.params)
+        self.flat_optims = []
+        self._note_optimizers()
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.n_local = torch.zeros((), dtype=torch.int64, device=self.dev)
         self.captured = {}
@@ -121,6 +128,18 @@ class GraphedTrainStep:
         self.graph_opt = None
         self.static_flat = None
         self.pool = None                     # graph memory pool shared by every captured shape
+
+    def _note_optimizers(self):
+        """optim.FlatAdam instances own the parameters' storage, their flat gradient buffers and the bf16 mirror"""
+        opts = list(self.opt_pair) if self.opt_pair is not None else ([self.optimizer] if self.optimizer is not None else [])
+        self.flat_optims = [o for o in opts if isinstance(o, FlatAdam)]
+        if self.flat_optims:
+            _optim.attach(self.model, self.flat_optims)
+
+    def _zero(self):
+        self.bucket.zero()
+        for o in self.flat_optims:
+            o.zero_grad()                  # one zero-fill of the flat gradient buffer; backward writes into it directly
 
     # ------------------------------------------------------------------ data
     @staticmethod
@@ -172,7 +191,7 @@ class GraphedTrainStep:
     # ------------------------------------------------------------------ the step
     def _forward_backward(self, c):
         self.seed_ctr.add_(1)
-        self.bucket.zero()
+        self._zero()
         if getattr(c, "packed", False):
             loss_sum, n_tok = self.model.forward_packed(c.pb, "train")
         else:
@@ -204,7 +223,27 @@ class GraphedTrainStep:
         self._stash = None
         memory.backward(leaf.grad)
 
+    def _bind_flat(self, c, which, params):
+        """After a capture: gradients the captured backward left OUTSIDE the optimizers' flat buffers (none when every
+        producer wrote through ops._gdest) are listed for an eager copy per replay; `.grad` of every parameter is then
+        pointed at its slice of the flat buffer, which is what the captured optimizer step reads."""
+        pairs = []
+        for o in self.flat_optims:
+            ids = {id(p) for p in params}
+            for p, gv in zip(o.params, o.gviews):
+                if id(p) in ids:
+                    if p.grad.data_ptr() != gv.data_ptr():
+                        pairs.append((gv, p.grad.reshape(gv.shape)))
+                    p.grad = gv
+        setattr(c, "copy_" + which, pairs)
+
+    @staticmethod
+    def _copy_pairs(pairs):
+        if pairs:
+            torch._foreach_copy_([d for d, _ in pairs], [s for _, s in pairs])
+
     def _capture_split(self, c):
+        flat = bool(self.flat_optims)
         c.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(c.graph, pool=self.pool):
             self._phase_a(c)
@@ -218,14 +257,28 @@ class GraphedTrainStep:
             self._phase_b()
         c.grads_b = [p.grad for p in self.params_b]
         assert all(g is not None for g in c.grads_a + c.grads_b), "a live parameter received no gradient"
+        if self.comm is None:
+            self.comm = torch.cuda.Stream()
+        if flat:
+            # optim.FlatAdam: the backward wrote the gradients into the optimizers' flat buffers, which are all-reduced
+            # in place; two optimizers, so that Adam of the head/decoder parameters also runs behind graph B
+            self._bind_flat(c, "a", self.params_a)
+            self._bind_flat(c, "b", self.params_b)
+            if self.graph_opt is None:
+                self.graph_opt = []
+                for o in self.opt_pair:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        o.step()
+                    self.graph_opt.append(g)
+            return
         if self.flat_a is None:
             self.flat_a = torch.cat([g.reshape(-1) for g in c.grads_a])
             self.flat_b = torch.cat([g.reshape(-1) for g in c.grads_b])
-            self.comm = torch.cuda.Stream()
-        for flat, params in ((self.flat_a, self.params_a), (self.flat_b, self.params_b)):
+        for flat_buf, params in ((self.flat_a, self.params_a), (self.flat_b, self.params_b)):
             off = 0
             for p in params:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                p.grad = flat_buf[off:off + p.numel()].view_as(p)
                 off += p.numel()
         if self.graph_opt is None:
             self.graph_opt = torch.cuda.CUDAGraph()
@@ -234,20 +287,34 @@ class GraphedTrainStep:
 
     def _replay_split(self, c):
         cur = torch.cuda.current_stream()
+        flat = bool(self.flat_optims)
         c.graph.replay()
         self.comm.wait_stream(cur)
-        with torch.cuda.stream(self.comm):               # head/decoder gradients: pack + all-reduce behind graph B
-            torch.cat([g.reshape(-1) for g in c.grads_a], out=self.flat_a)
-            if self.world > 1:
-                dist.all_reduce(self.flat_a, group=self.group)
+        with torch.cuda.stream(self.comm):               # head/decoder gradients: all-reduce (+ Adam) behind graph B
+            if flat:
+                self._copy_pairs(c.copy_a)
+                if self.world > 1:
+                    dist.all_reduce(self.opt_pair[0].g, group=self.group)
+                self.graph_opt[0].replay()
+            else:
+                torch.cat([g.reshape(-1) for g in c.grads_a], out=self.flat_a)
+                if self.world > 1:
+                    dist.all_reduce(self.flat_a, group=self.group)
         c.graph_b.replay()
         self.comm.wait_stream(cur)
         with torch.cuda.stream(self.comm):
-            torch.cat([g.reshape(-1) for g in c.grads_b], out=self.flat_b)
-            if self.world > 1:
-                dist.all_reduce(self.flat_b, group=self.group)
+            if flat:
+                self._copy_pairs(c.copy_b)
+                if self.world > 1:
+                    dist.all_reduce(self.opt_pair[1].g, group=self.group)
+                self.graph_opt[1].replay()
+            else:
+                torch.cat([g.reshape(-1) for g in c.grads_b], out=self.flat_b)
+                if self.world > 1:
+                    dist.all_reduce(self.flat_b, group=self.group)
         cur.wait_stream(self.comm)
-        self.graph_opt.replay()
+        if not flat:
+            self.graph_opt.replay()
 
     def _count_tokens_eager(self, c):
         if self.world > 1:
@@ -255,27 +322,36 @@ class GraphedTrainStep:
             self.n_global.copy_((lab != 0).sum().to(torch.float32).reshape(1))
             dist.all_reduce(self.n_global, group=self.group)
 
+    def _make_pair(self, c):
+        """find the two parameter groups with one split backward, then build the two optimizers"""
+        self._phase_a(c)
+        pa = [p for p in self.bucket.params if p.grad is not None]
+        ids = {id(p) for p in pa}
+        pb = [p for p in self.bucket.params if id(p) not in ids]
+        self._phase_b()
+        self.params_a, self.params_b = pa, pb
+        self.opt_pair = (self.opt_factory(pa), self.opt_factory(pb))
+        self.optimizer = _OptimizerPair(self.opt_pair)
+        self._note_optimizers()
+        if self.opt_overlap:
+            self.opt_stream = torch.cuda.Stream()
+
     def _eager_step(self, c):
         """A normal (uncaptured) training step: initialises the optimizer state and all lazy CUDA state."""
         self._count_tokens_eager(c)
-        if self.opt_overlap and self.opt_pair is None:
-            # find the two parameter groups with one split backward, then train with two optimizers from the start
-            self._phase_a(c)
-            pa = [p for p in self.bucket.params if p.grad is not None]
-            ids = {id(p) for p in pa}
-            pb = [p for p in self.bucket.params if id(p) not in ids]
-            self._phase_b()
-            self.params_a, self.params_b = pa, pb
-            self.opt_pair = (self.opt_factory(pa), self.opt_factory(pb))
-            self.optimizer = _OptimizerPair(self.opt_pair)
-            self.opt_stream = torch.cuda.Stream()
-            self.opt_pair[0].step()
-            self.opt_pair[1].step()
-            self.opt_ready = True
-            return
+        if self.two_opts and self.opt_pair is None:
+            self._make_pair(c)             # the gradients of this pass predate the optimizers' flat buffers: discard them
+            self._zero()
         self._forward_backward(c)
         if self.world > 1:
-            self.bucket.all_reduce(self.group)
+            if self.flat_optims:
+                for o in self.opt_pair:
+                    o.gather_grads()
+                    dist.all_reduce(o.g, group=self.group)
+                    for p, gv in zip(o.params, o.gviews):
+                        p.grad = gv
+            else:
+                self.bucket.all_reduce(self.group)
         self.optimizer.step()
         self.opt_ready = True
 
@@ -291,14 +367,14 @@ class GraphedTrainStep:
             self._forward_backward(c)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.bucket.zero()
+        self._zero()
         if self.pool is None and os.environ.get("FIRA_GRAPH_PRIVATE_POOLS", "0") != "1":
             self.pool = torch.cuda.graph_pool_handle()
         if self.split:
             return self._capture_split(c)
         c.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(c.graph, pool=self.pool):
-            if self.world == 1 and self.opt_pair is not None:
+            if self.world == 1 and self.opt_overlap:
                 # ONE graph, two branches: Adam on the head/decoder parameters (3/4 of the bytes, memory-bound, nothing
                 # else could hide it at the end of the step) runs on a side stream WHILE the encoder backward runs
                 self._phase_a(c)
@@ -347,6 +423,9 @@ class GraphedTrainStep:
             return self.loss_sum, self.n_local
         if c.graph is None:
             self._capture(c)
+        for o in self.flat_optims:                    # parameters set from outside (load_state_dict): refresh the bf16 mirror
+            if not o.fresh:
+                o.sync_mirror()
         self._count_tokens_eager(c)
         if self.split:
             self._replay_split(c)

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import optim as _optim
 from .modules import Decoder, Encoder, _i32, _u8
 
 
@@ -80,6 +81,24 @@ class TransModel(nn.Module):
         dead = {id(p) for p in self.dead_parameters()}
         return [p for p in self.parameters() if id(p) not in dead]
 
+    def flat_groups(self):
+        """Parameters optim.FlatAdam should lay out back to back, so that the concatenated weights of the fused
+        projections (q|k of a Combination, q|k|v of a self-attention, the 12 cross-attention k|v projections) and the
+        (weight, bias) pair of every LayerNorm are single views of its flat buffers."""
+        g = []
+        for comb, gcn in zip(self.encoder.combination_list2, self.encoder.gcn_list):
+            l = comb.linear_layers
+            g += [[l[0].weight, l[1].weight], [l[0].bias, l[1].bias], [comb.layernorm.weight, comb.layernorm.bias],
+                  [gcn.layernorm.weight, gcn.layernorm.bias]]
+        dec = self.decoder
+        for a, c, f in zip(dec.attention_list, dec.cross_attention_list, dec.feed_forward_list):
+            g += [[a.fc_q.weight, a.fc_k.weight, a.fc_v.weight], [a.fc_q.bias, a.fc_k.bias, a.fc_v.bias],
+                  [a.layernorm.weight, a.layernorm.bias], [c.layernorm.weight, c.layernorm.bias],
+                  [f.layernorm.weight, f.layernorm.bias]]
+        g.append([t for c in dec.cross_attention_list for t in (c.fc_k.weight, c.fc_v.weight)])
+        g.append([t for c in dec.cross_attention_list for t in (c.fc_k.bias, c.fc_v.bias)])
+        return g
+
     @staticmethod
     def shifted_label(tar_label):
         """Model.py:71-79: labels shifted left by one with a trailing 0."""
@@ -92,6 +111,8 @@ class TransModel(nn.Module):
         (Dataset.py:80-94).  Loss, token count and gradients equal forward() on the padded batch; 'dev' ids number
         copy positions by the commit's own memory rows (V + m, m < code rows + sub-token rows)."""
         bf16 = self.precision == "bf16"
+        if bf16:
+            _optim.ensure_fresh(self)
         self.decoder.prefetch_weights()
         pf_head = ops.prefetch_head(bf16, self.out_fc.weight, self.copy_net.LinearSource.weight,
                                     self.copy_net.LinearTarget.weight)
@@ -114,6 +135,8 @@ class TransModel(nn.Module):
             t.to(dev, non_blocking=True) for t in (sou, tar, mark, ast_change, tar_label, sub_token))
         mem_mask = torch.cat((sou != 0, sub_token != 0), dim=1)
         bf16 = self.precision == "bf16"
+        if bf16:
+            _optim.ensure_fresh(self)            # parameters re-homed by optim.FlatAdam: bf16 mirror up to date
         self.decoder.prefetch_weights()          # decoder / head weight preparation overlaps with the encoder
         pf_head = ops.prefetch_head(bf16, self.out_fc.weight, self.copy_net.LinearSource.weight,
                                     self.copy_net.LinearTarget.weight) if sou.is_cuda else None

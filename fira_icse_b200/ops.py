@@ -20,6 +20,7 @@ import os
 import torch
 
 from . import _lib
+from . import optim as _optim
 from ._lib import FIRA_BF16, FIRA_F32, call
 
 D = 256
@@ -50,6 +51,18 @@ def _require_cuda(*ts):
 
 def _ceil(a, b):
     return (a + b - 1) // b
+
+
+def _gdest(ts, shape, zero=False):
+    """fp32 buffer for the gradient of parameter(s) `ts`: a view of the optimizer's flat gradient buffer when the
+    parameters are re-homed by optim.FlatAdam (already zero-filled, adopted by autograd without a copy), else a new
+    tensor (`zero`: the producer accumulates atomically)."""
+    if not isinstance(ts, (list, tuple)):
+        ts = (ts,)
+    v = _optim.grad_dest(ts, shape)
+    if v is not None:
+        return v
+    return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=ts[0].device)
 
 
 # ----------------------------------------------------------------------------- fp32 GEMM (parity mode)
@@ -93,9 +106,9 @@ def linear_dx(dy, ld_dy, W, M, out=None, accumulate=False, dy_off=0, n=None):
     return out
 
 
-def linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0):
+def linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0, out=None):
     """fp32: dW[N,K] = dy[M,N]^T x[M,K]."""
-    dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    dW = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
     gemm_raw(_ptr(dy, dy_off), ld_dy, 0, _ptr(x, x_off), ldx, 0, _ptr(dW), K, N, K, M)
     return dW
 
@@ -117,10 +130,12 @@ def _tc_splits(tiles, kblocks):
     return max(1, min(kblocks // 8 if kblocks >= 16 else 1, _ceil(148, tiles)))
 
 
-def colsum(x, ld, M, N, weight=None, x_off=0, dtype=None):
+def colsum(x, ld, M, N, weight=None, x_off=0, dtype=None, out=None):
+    """out[n] (+)= sum_m w[m] x[m, n]; `out` must be zero-filled (atomic accumulation)"""
     if dtype is None:
         dtype = FIRA_BF16 if x.dtype == torch.bfloat16 else FIRA_F32
-    out = torch.zeros(N, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.zeros(N, dtype=torch.float32, device=x.device)
     call("fira_colsum", _ptr(x, x_off), ld, M, N, _ptr(weight), _ptr(out), dtype, _stream())
     return out
 
@@ -142,6 +157,9 @@ class Prec:
         """GEMM-operand form of a parameter: itself (fp32 mode) or a bf16 copy cached for fwd+bwd."""
         if not self.bf16:
             return W
+        m = _optim.mirror_of(W)                 # parameters re-homed by optim.FlatAdam: a view of its bf16 mirror
+        if m is not None:
+            return m
         k = (W.data_ptr(), tuple(W.shape))
         if k not in self.wcache:
             self.wcache[k] = (W, W.detach().to(torch.bfloat16))     # keep W alive: the key is its address
@@ -169,10 +187,10 @@ class Prec:
         return gemm_tc(dy, ld_dy, 1, self.w(W), K, 0, out, K, M, K, N, accumulate=accumulate, a_off=dy_off)
 
     # dW = dy^T x   (fp32 result in both modes)
-    def linear_dw(self, dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0):
+    def linear_dw(self, dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0, out=None):
         if not self.bf16:
-            return linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=dy_off, x_off=x_off)
-        dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+            return linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=dy_off, x_off=x_off, out=out)
+        dW = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
         bn = 256 if K > 128 else (128 if K > 64 else 64)
         splits = _tc_splits(_ceil(N, 128) * _ceil(K, bn), _ceil(M, 64))
         return gemm_tc(dy, ld_dy, 0, x, ldx, 0, dW, K, N, K, M, splits=splits, a_off=dy_off, b_off=x_off)
@@ -183,11 +201,14 @@ class Prec:
              _ptr(stats), _ptr(stats, rows), rows, D, float(p), seed, _ptr(self.seed_ctr), sid, self.code, _stream())
         return stats
 
-    def ln_bwd(self, dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=None, accum=False):
+    def ln_bwd(self, dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=None, accum=False, beta=None):
+        """beta: the LayerNorm bias parameter; with (gamma, beta) re-homed back to back by optim.FlatAdam their
+        gradients are accumulated straight into its flat gradient buffer"""
         dz = torch.empty_like(z)
         if d_resid is None:
             d_resid = torch.empty_like(z)
-        dgb = torch.zeros((2, D), dtype=torch.float32, device=z.device)
+        dgb = _gdest((gamma, beta), (2, D), zero=True) if beta is not None else \
+            torch.zeros((2, D), dtype=torch.float32, device=z.device)
         call("fira_ln_residual_bwd", _ptr(dA), _ptr(dB), split, _ptr(z), _ptr(resid), _ptr(stats), _ptr(stats, rows),
              _ptr(gamma), _ptr(dz), _ptr(d_resid), int(accum), _ptr(dgb), _ptr(dgb, D), rows, D, float(p), seed,
              _ptr(self.seed_ctr), sid, self.code, _stream())
@@ -207,35 +228,53 @@ def ln_bwd(dA, dB, split, z, resid, stats, gamma, rows, p, seed, sid, d_resid=No
 
 
 _SIDE_STREAMS = {}
+# side work of a backward pass is many INDEPENDENT groups of small launches (a weight-gradient GEMM + its bias column
+# sums + fp32 adjoints of the weight merges): on one side stream they serialise into a chain that is longer than the
+# input-gradient chain of the main stream (timeline of GPU run F: 2.3 ms of the 4.1 ms step on that stream), so the
+# groups rotate over several streams = parallel branches of the captured graph
+N_SIDE = max(1, int(os.environ.get("FIRA_SIDE_STREAMS", "8")))
+# the 256^3 fp32 products of the GCN weight merge (W2 W1 and its two adjoints) are 16 CTAs of the 64 x 64 tile: split-K
+# spreads them over 64 CTAs (15.9 us per product in the step timeline); bf16 mode only -- the fp32 parity mode keeps the
+# deterministic single-pass sum
+MERGE_SPLITS = max(1, int(os.environ.get("FIRA_MERGE_SPLITS", "4")))
+_TURN = [0]            # rotation shared by every Fork, so consecutive Forks do not all start on the same stream
 
 
 class Fork:
-    """Runs the weight-gradient / bias-gradient work of a backward pass on a side stream.
+    """Runs the weight-gradient / bias-gradient work of a backward pass on side streams.
 
     In a backward step `dZ` feeds three independent consumers: the input-gradient GEMM (critical
     path), the weight-gradient GEMM and the bias column sums.  The last two use a handful of CTAs
-    each; issued on a second stream they overlap with the critical path (and become parallel
-    branches when the step is captured into a CUDA graph).  Tensors read on the side stream are kept
-    alive until join(), tensors produced there are only consumed after join()."""
+    each; issued on other streams they overlap with the critical path (and become parallel
+    branches when the step is captured into a CUDA graph).  Every `with fork(...)` group takes the next
+    side stream in rotation.  Tensors read on a side stream are kept alive until join(), tensors produced
+    there are only consumed after join()."""
 
-    def __init__(self, device):
+    def __init__(self, device, n_side=None):
         self.main = torch.cuda.current_stream(device)
         key = (device.index if device.index is not None else torch.cuda.current_device())
         if key not in _SIDE_STREAMS:
-            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-        self.side = _SIDE_STREAMS[key]
+            _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(N_SIDE)]
+        self.sides = _SIDE_STREAMS[key][:n_side] if n_side else _SIDE_STREAMS[key]
+        self.side = self.sides[0]
         self.keep = []
-        self.used = False
+        self.used = set()
 
-    def __call__(self, *tensors):
+    def __call__(self, *tensors, lane=None):
+        """lane: pin the group to one side stream (groups that accumulate into the same tensor must serialise)"""
         self.keep.extend(tensors)
+        if lane is None:
+            lane = _TURN[0]
+            _TURN[0] += 1
+        self.side = self.sides[lane % len(self.sides)]
         self.side.wait_stream(self.main)
-        self.used = True
+        self.used.add(self.side)
         return torch.cuda.stream(self.side)
 
     def join(self):
-        if self.used:
-            self.main.wait_stream(self.side)
+        for s in self.used:
+            self.main.wait_stream(s)
+        self.used.clear()
         self.keep.clear()
 
 
@@ -249,19 +288,19 @@ class Prefetch:
         self.event = None
 
 
-def _prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2):
+def _prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2, fused=True):
     f32 = dict(dtype=torch.float32, device=Wq.device)
-    Wqk = torch.cat((Wq, Wk), 0)
-    bqk = torch.cat((bq, bk), 0)
+    Wqk = _optim.cat_rows((Wq, Wk))                                  # views when optim.FlatAdam laid them out back to back
+    bqk = _optim.cat_rows((bq, bk))
     Vtab = linear(mark_emb, Wv, bv)                                # fp32 [4, 256]: value has 4 distinct rows
     Wc = torch.empty((D, D), **f32)                                # W2 @ W1
-    gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=1)
+    gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=MERGE_SPLITS if pr.bf16 else 1)
     c1 = torch.empty((D,), **f32)                                  # W2 @ b1
     gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
     for w in (Wqk, Wo, Wc):
         pr.w(w)                                                    # bf16 operand copies (no-op in fp32 mode)
     # the fused GCN backward multiplies by Wc itself ([out, in] read as K = out): its B operand is Wc^T stored K-major
-    WcT16 = Wc.t().contiguous().to(torch.bfloat16) if pr.bf16 else None
+    WcT16 = Wc.t().contiguous().to(torch.bfloat16) if (pr.bf16 and fused) else None
     return Wqk, bqk, Vtab, Wc, c1, WcT16
 
 
@@ -273,14 +312,14 @@ def prefetch_decoder(bf16, lp, device):
     L = len(lp) // DEC_LAYER_PARAMS
     fork = Fork(device)
     with fork(*lp):
-        Wkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])], 0)     # [L*512, 256]
-        bkv = torch.cat([t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])], 0)
+        Wkv = _optim.cat_rows([t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])])     # [L*512, 256]
+        bkv = _optim.cat_rows([t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])])
         pr.w(Wkv)
         layers = []
         for i in range(L):
             q = lp[i * 26:(i + 1) * 26]
-            Wqkv = torch.cat((q[0], q[2], q[4]), 0)
-            bqkv = torch.cat((q[1], q[3], q[5]), 0)
+            Wqkv = _optim.cat_rows((q[0], q[2], q[4]))
+            bqkv = _optim.cat_rows((q[1], q[3], q[5]))
             for w in (Wqkv, q[6], q[10], q[16], q[20], q[22]):     # Wqkv, self Wo, cross Wq, cross Wo, W1, W2
                 pr.w(w)
             layers.append((Wqkv, bqkv))
@@ -361,10 +400,10 @@ class EncoderFn(torch.autograd.Function):
         # layer i's event right before it needs it, so only the first layer's ~8 tiny launches are exposed
         fork = Fork(dev)
         preps, events = [], []
-        with fork(mark_emb, *lp):
-            for i in range(L):
+        for i in range(L):
+            with fork(mark_emb, *lp[i * 16:(i + 1) * 16]):
                 Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
-                preps.append(_prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2))
+                preps.append(_prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2, fused=fused))
                 ev = torch.cuda.Event()
                 ev.record()
                 events.append(ev)
@@ -426,7 +465,7 @@ class EncoderFn(torch.autograd.Function):
         dXc = pr.empty((Mc, D), dev)
         dGin = pr.empty((R, D), dev)
         call("fira_unpack_memory", _ptr(d_mem), _ptr(dXc), _ptr(dGin), B, n_code, n_sub, n_ast, D, pr.code, st)
-        d_mark_emb = torch.zeros_like(mark_emb)
+        d_mark_emb = _gdest(mark_emb, tuple(mark_emb.shape), zero=True)
         grads = [None] * len(lp)
         fork = Fork(dev)
         for i in reversed(range(L)):
@@ -434,7 +473,7 @@ class EncoderFn(torch.autograd.Function):
             Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1, WcT16 = ctx.saved[i]
             sid = cfg["stream_base"] + i * 8
             # ---- GCN backward
-            dZ, dRes, d_glw, d_glb = pr.ln_bwd(dXc, dGin, Mc, Z, Gin, st_g, glw, R, p_gcn, seed, sid + 2)
+            dZ, dRes, d_glw, d_glb = pr.ln_bwd(dXc, dGin, Mc, Z, Gin, st_g, glw, R, p_gcn, seed, sid + 2, beta=glb)
             dGin_i = pr.empty((R, D), dev)
             if fused:
                 # one kernel: AdZ = A^T dZ (kept for the weight gradients), dGin_i = AdZ Wc + dRes
@@ -442,7 +481,7 @@ class EncoderFn(torch.autograd.Function):
                 call("fira_gcn_layer_bwd", _ptr(etrows[0]), _ptr(etrows[1]), _ptr(etrows[2]), _ptr(dZ), _ptr(WcT16),
                      _ptr(dRes), _ptr(AdZ), _ptr(dGin_i), R, D, st)
             with fork(dZ, G, rs, W1, W2, b1):
-                d_b2 = colsum(dZ, D, R, D)
+                d_b2 = colsum(dZ, D, R, D, out=_gdest(b2, (D,), zero=True))
                 if fused:                       # dZ^T (A H) = (A^T dZ)^T H ;  sum_i rowsum(A)_i dZ_i = colsum(A^T dZ)
                     fork.keep.append(AdZ)
                     d_c1 = colsum(AdZ, D, R, D)
@@ -450,11 +489,11 @@ class EncoderFn(torch.autograd.Function):
                 else:
                     d_c1 = colsum(dZ, D, R, D, weight=rs)
                     dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
-                d_W2 = torch.empty((D, D), **f32)       # dWc W1^T + d_c1 b1^T
-                gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=1)
-                d_W1 = torch.empty((D, D), **f32)       # W2^T dWc
-                gemm_raw(_ptr(W2), D, 0, _ptr(dWc), D, 0, _ptr(d_W1), D, D, D, D, splits=1)
-                d_b1 = torch.empty((D,), **f32)         # W2^T d_c1
+                d_W2 = _gdest(W2, (D, D))               # dWc W1^T + d_c1 b1^T
+                gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=MERGE_SPLITS if pr.bf16 else 1)
+                d_W1 = _gdest(W1, (D, D))               # W2^T dWc
+                gemm_raw(_ptr(W2), D, 0, _ptr(dWc), D, 0, _ptr(d_W1), D, D, D, D, splits=MERGE_SPLITS if pr.bf16 else 1)
+                d_b1 = _gdest(b1, (D,))                 # W2^T d_c1
                 gemm_raw(_ptr(W2), D, 0, _ptr(d_c1), 1, 0, _ptr(d_b1), 1, D, 1, D, splits=1)
                 fork.keep.extend((dWc, d_c1))
             if not fused:
@@ -464,28 +503,28 @@ class EncoderFn(torch.autograd.Function):
             # ---- Combination backward (rows < Mc of dGin_i are d(comb output))
             dXc_n = pr.empty((Mc, D), dev)
             dZc, _, d_clw, d_clb = pr.ln_bwd(dGin_i, dGin_i, Mc, Zc, Xc, st_c, clw, Mc, p_comb, seed, sid + 1,
-                                             d_resid=dXc_n)
+                                             d_resid=dXc_n, beta=clb)
             with fork(dZc, Cd):
-                d_bo = colsum(dZc, D, Mc, D)
-                d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D)
+                d_bo = colsum(dZc, D, Mc, D, out=_gdest(bo, (D,), zero=True))
+                d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D, out=_gdest(Wo, (D, D)))
             dCd = pr.linear_dx(dZc, D, Wo, Mc)
             dQK = pr.empty((Mc, 2 * D), dev)
             dVtab = torch.zeros((4, D), **f32)
             call("fira_comb_gate_bwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(dCd), _ptr(dQK), _ptr(dVtab),
                  Mc, D, D // heads, float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
-            with fork(dQK, Xc, dVtab, mark_emb, Wv, d_mark_emb):
-                d_bqk = colsum(dQK, 2 * D, Mc, 2 * D)
-                d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D)
-                d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D)
-                d_bv = colsum(dVtab, D, 4, D)
+            with fork(dQK, Xc, dVtab, mark_emb, Wv, d_mark_emb, lane=0):     # d_mark_emb accumulates across layers
+                d_bqk = colsum(dQK, 2 * D, Mc, 2 * D, out=_gdest((bq, bk), (2 * D,), zero=True))
+                d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D, out=_gdest((Wq, Wk), (2 * D, D)))
+                d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D, out=_gdest(Wv, (D, D)))
+                d_bv = colsum(dVtab, D, 4, D, out=_gdest(bv, (D,), zero=True))
                 linear_dx(dVtab, D, Wv, 4, out=d_mark_emb, accumulate=True)
             pr.linear_dx(dQK, 2 * D, Wqk, Mc, out=dXc_n, accumulate=True)
             grads[i * 16:(i + 1) * 16] = [d_Wqk[:D], d_bqk[:D], d_Wqk[D:], d_bqk[D:], d_Wv, d_bv, d_Wo, d_bo,
                                           d_clw, d_clb, d_W1, d_b1, d_W2, d_b2, d_glw, d_glb]
             dXc, dGin = dXc_n, dGin_i
             ctx.saved[i] = None
-        d_emb = torch.zeros_like(emb)
-        d_ast = torch.zeros_like(ast_emb)
+        d_emb = _gdest(emb, tuple(emb.shape), zero=True)
+        d_ast = _gdest(ast_emb, tuple(ast_emb.shape), zero=True)
         call("fira_embed_nodes_bwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(dXc), _ptr(dGin),
              _ptr(d_emb), _ptr(d_ast), B, n_code, n_sub, n_ast, D, pr.code, st)
         fork.join()
@@ -598,21 +637,21 @@ class DecoderFn(torch.autograd.Function):
             X, Wqkv, QKV, ctx1, st1, Z1, ls1, X1, Q, ctx2, st2, Z2, ls2, X2, Hh, Z3, ls3 = ctx.saved[i]
             sid = cfg["stream_base"] + 64 + i * 8
             # ---- FFN
-            dZ3, dX2, d_flw, d_flb = pr.ln_bwd(dX, dX, Mt, Z3, X2, ls3, flw, Mt, p, seed, sid + 2)
+            dZ3, dX2, d_flw, d_flb = pr.ln_bwd(dX, dX, Mt, Z3, X2, ls3, flw, Mt, p, seed, sid + 2, beta=flb)
             with fork(dZ3, Hh):
-                d_fb2 = colsum(dZ3, D, Mt, D)
-                d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F)
+                d_fb2 = colsum(dZ3, D, Mt, D, out=_gdest(fb2, (D,), zero=True))
+                d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F, out=_gdest(fW2, (D, F)))
             dHh = pr.linear_dx(dZ3, D, fW2, Mt)                           # [Mt, 1024]
             call("fira_relu_bwd", _ptr(Hh), _ptr(dHh), Mt * F, pr.code, st)
             with fork(dHh, X2):
-                d_fb1 = colsum(dHh, F, Mt, F)
-                d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D)
+                d_fb1 = colsum(dHh, F, Mt, F, out=_gdest(fb1, (F,), zero=True))
+                d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D, out=_gdest(fW1, (F, D)))
             pr.linear_dx(dHh, F, fW1, Mt, out=dX2, accumulate=True)
             # ---- cross-attention
-            dZ2, dX1, d_clw, d_clb = pr.ln_bwd(dX2, dX2, Mt, Z2, X1, ls2, clw, Mt, p, seed, sid + 1)
+            dZ2, dX1, d_clw, d_clb = pr.ln_bwd(dX2, dX2, Mt, Z2, X1, ls2, clw, Mt, p, seed, sid + 1, beta=clb)
             with fork(dZ2, ctx2):
-                d_cbo = colsum(dZ2, D, Mt, D)
-                d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D)
+                d_cbo = colsum(dZ2, D, Mt, D, out=_gdest(cbo, (D,), zero=True))
+                d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D, out=_gdest(cWo, (D, D)))
             dctx2 = pr.linear_dx(dZ2, D, cWo, Mt)
             dQ = pr.empty((Mt, D), dev)
             if pk is not None:
@@ -624,22 +663,22 @@ class DecoderFn(torch.autograd.Function):
                      _ptr(mem_mask), 0, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
                      _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
             with fork(dQ, X1):
-                d_cbq = colsum(dQ, D, Mt, D)
-                d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D)
+                d_cbq = colsum(dQ, D, Mt, D, out=_gdest(cbq, (D,), zero=True))
+                d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D, out=_gdest(cWq, (D, D)))
             pr.linear_dx(dQ, D, cWq, Mt, out=dX1, accumulate=True)
             # ---- self-attention
-            dZ1, dX0, d_slw, d_slb = pr.ln_bwd(dX1, dX1, Mt, Z1, X, ls1, slw, Mt, p, seed, sid + 0)
+            dZ1, dX0, d_slw, d_slb = pr.ln_bwd(dX1, dX1, Mt, Z1, X, ls1, slw, Mt, p, seed, sid + 0, beta=slb)
             with fork(dZ1, ctx1):
-                d_sbo = colsum(dZ1, D, Mt, D)
-                d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D)
+                d_sbo = colsum(dZ1, D, Mt, D, out=_gdest(sbo, (D,), zero=True))
+                d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D, out=_gdest(sWo, (D, D)))
             dctx1 = pr.linear_dx(dZ1, D, sWo, Mt)
             dQKV = pr.empty((Mt, 3 * D), dev)
             call("fira_attn_bwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
                  _ptr(ctx1), _ptr(dctx1), D, _ptr(st1), _ptr(dQKV), 3 * D, _ptr(dQKV, D), 3 * D, _ptr(dQKV, 2 * D), 3 * D,
                  B, H, T, T, D // H, pr.code, st)
             with fork(dQKV, X):
-                d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D)
-                d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D)
+                d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D, out=_gdest((sbq, sbk, sbv), (3 * D,), zero=True))
+                d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D, out=_gdest((sWq, sWk, sWv), (3 * D, D)))
             pr.linear_dx(dQKV, 3 * D, Wqkv, Mt, out=dX0, accumulate=True)
             grads[i * 26:(i + 1) * 26] = [
                 d_Wqkv[:D], d_bqkv[:D], d_Wqkv[D:2 * D], d_bqkv[D:2 * D], d_Wqkv[2 * D:], d_bqkv[2 * D:],
@@ -651,14 +690,16 @@ class DecoderFn(torch.autograd.Function):
         # hoisted K/V projections of the memory: one weight-grad GEMM, one input-grad GEMM
         mem2 = memory.view(Ms, D)
         with fork(dKV, mem2):
-            d_bkv = colsum(dKV, ldkv, Ms, ldkv)
-            d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D)
+            kv_w = [t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])]
+            kv_b = [t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])]
+            d_bkv = colsum(dKV, ldkv, Ms, ldkv, out=_gdest(kv_b, (ldkv,), zero=True))
+            d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D, out=_gdest(kv_w, (ldkv, D)))
         d_mem = pr.linear_dx(dKV, ldkv, Wkv, Ms).view(memory.shape).to(mem_dtype)
         for i in range(L):
             o = i * 2 * D
             grads[i * 26 + 12], grads[i * 26 + 13] = d_Wkv[o:o + D], d_bkv[o:o + D]
             grads[i * 26 + 14], grads[i * 26 + 15] = d_Wkv[o + D:o + 2 * D], d_bkv[o + D:o + 2 * D]
-        d_emb = torch.zeros_like(dec_emb)
+        d_emb = _gdest(dec_emb, tuple(dec_emb.shape), zero=True)
         call("fira_embed_rows_bwd", _ptr(tar), _ptr(dX), _ptr(d_emb), Mt, D, pr.code, st)
         fork.join()
         return (None, None, d_mem, None, None, None, d_emb, *grads)
@@ -722,7 +763,7 @@ class HeadFn(torch.autograd.Function):
              _ptr(stats), _ptr(nll), _ptr(amax), Mt, T, V, S, pr.code, st)
         ctx.misc = (pr, memory2, dec2, dec32, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V,
                     memory.dtype, dec.dtype, pk, memory.shape)
-        ctx.save_for_backward(Wout, Ws, Wt, Wres, Wp)
+        ctx.save_for_backward(Wout, Ws, Wt, Wres, Wp, bout, bres, bp)
         loss_sum = colsum(nll, 1, Mt, 1).view(())
         ids = amax.view(B, T) if want_argmax else None
         nll2 = nll.view(B, T)
@@ -733,7 +774,7 @@ class HeadFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_nll, g_ids):
         (pr, memory2, dec2, dec32, mem_mask, label, logits, ldl, src, tgt, sc, stats, B, T, S, V,
          mem_dt, dec_dt, pk, mem_shape) = ctx.misc
-        Wout, Ws, Wt, Wres, Wp = ctx.saved_tensors
+        Wout, Ws, Wt, Wres, Wp, bout, bres, bp = ctx.saved_tensors
         Mt, Ms = B * T, memory2.shape[0]
         dev = dec2.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -748,8 +789,8 @@ class HeadFn(torch.autograd.Function):
         # pointer scores
         d_src = pr.empty((Ms, D), dev)
         d_tgt = torch.zeros((Mt, D), **f32)
-        d_wres = torch.zeros((1, D), **f32)
-        d_bres = torch.zeros((1,), **f32)
+        d_wres = _gdest(Wres, (1, D), zero=True)
+        d_bres = _gdest(bres, (1,), zero=True)
         if pk is not None:
             call("fira_zero_pad_rows", _ptr(d_src), D, D, _ptr(pk.off), B, pk.Rc, pk.Rs, pr.code, st)
             call("fira_copy_scores_packed_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(pk.ranges),
@@ -759,12 +800,12 @@ class HeadFn(torch.autograd.Function):
                  _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
         fork = Fork(dev)
         with fork(d_src, memory2, dlogits, dec2, dgl, dec32, d_tgt):
-            d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D)
-            d_bout = colsum(dlogits, ldl, Mt, V)
-            d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D)
-            d_bp = colsum(dgl, 2, Mt, 2)
-            d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D)
-            d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D)
+            d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D, out=_gdest(Ws, (D, D)))
+            d_bout = colsum(dlogits, ldl, Mt, V, out=_gdest(bout, (V,), zero=True))
+            d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D, out=_gdest(Wout, (V, D)))
+            d_bp = colsum(dgl, 2, Mt, 2, out=_gdest(bp, (2,), zero=True))
+            d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D, out=_gdest(Wp, (2, D)))
+            d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D, out=_gdest(Wt, (D, D)))
         d_mem = pr.linear_dx(d_src, D, Ws, Ms)
         # vocabulary projection (the big one), gate and target projection; d_dec accumulates in fp32
         if pr.bf16:

@@ -52,9 +52,13 @@ class DataParallelStep:
         live = model.live_parameters() if hasattr(model, "live_parameters") else list(model.parameters())
         self.bucket = FlatGradBucket(live)
         self.optimizer = optimizer_factory(self.bucket.params)
+        from .optim import FlatAdam, attach
+        if isinstance(self.optimizer, FlatAdam):
+            attach(model, [self.optimizer])
 
     def step(self, batch, stage="train"):
         self.bucket.zero()
+        self.optimizer.zero_grad(set_to_none=True)       # optim.FlatAdam: also zero-fills its flat gradient buffer
         loss_sum, n_tok = self.model(*batch, stage)
         n_global = n_tok.to(torch.float32).reshape(1).clone()
         loss_global = loss_sum.detach().reshape(1).clone()

@@ -41,8 +41,9 @@ const char* fira_last_error_string(void);
 int fira_built_arch(void);                 /* 100 when compiled for sm_100a */
 /* Launch mode of every kernel of the library (the one process-wide switch, atomic): on = programmatic dependent
  * launch -- a kernel's CTAs are scheduled while the previous kernel of the stream drains and block in
- * griddepcontrol.wait before their first global-memory access (results are identical; launch gaps shrink).
- * Default: on, FIRA_PDL=0 in the environment turns it off. */
+ * griddepcontrol.wait before their first global-memory access (results are identical).
+ * Default: on (FIRA_PDL=0 in the environment turns it off).  Measured on the captured training step (profiles/):
+ * 3.23 -> 3.05 ms once the side work runs on several streams; with ONE side stream it was 3% slower. */
 int fira_set_pdl(int on);
 int fira_get_pdl(void);
 
@@ -64,6 +65,11 @@ int fira_gemm_f32(const float* A, long lda, int a_kcontig, const float* B, long 
 int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
                       long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
                       const float* rc, int relu, int accumulate, int splits, void* stream);
+
+/* Debugging aid (tools/gemm_probe.py): with a device buffer of >= 16 uint64 set, CTA (0,0,0) of every following
+ * fira_gemm_bf16_tc launch stamps %globaltimer at its phase boundaries (entry, prologue, dependency wait, TMA issued,
+ * first stage landed, MMAs issued, accumulator ready, stores issued, exit); NULL switches it off (the default). */
+int fira_debug_set_probe(void* probe);
 
 /* ---- embeddings -------------------------------------------------------------------------------
  * Encoder node features in segment-major order (all code rows, all sub-token rows, all AST/edit
@@ -118,6 +124,17 @@ int fira_comb_gate3_bwd(const void* q, const void* k, const void* v, const void*
 int fira_relu_bwd(const void* h, void* d, long n, int dtype, void* stream);
 /* out[n] += sum_m w[m] * x[m,n]  (w == NULL -> 1): bias gradients. */
 int fira_colsum(const void* x, long ld, long M, int N, const float* row_weight, float* out, int dtype, void* stream);
+
+/* ---- optimizer step (run_model.py:101-109: `optimizer.step()` of torch.optim.Adam(lr), no weight decay / amsgrad) over
+ *      ONE flat fp32 parameter buffer (fira_icse_b200/optim.py re-homes the model's parameters in it), one launch:
+ *        g' = g / *grad_scale (grad_scale NULL -> 1);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *        p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),  t = *step (device fp32 scalar, the caller has
+ *        already incremented it);  p_bf16 (may be NULL) receives the bf16 copy of the updated parameters (the GEMM
+ *        operands of the throughput mode).  n: multiple of 8; all buffers 16-byte aligned. */
+int fira_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, long n, float lr, float beta1, float beta2,
+                   float eps, const float* step, const float* grad_scale, void* stream);
+/* y = bf16(x), n a multiple of 8 (refresh of the bf16 parameter mirror after parameters were set from outside). */
+int fira_cast_bf16(const float* x, void* y, long n, void* stream);
 
 /* memory = cat(code rows, sub-token rows) per commit (Model.py:48) and its adjoint. */
 int fira_pack_memory(const void* code, const void* rest, void* mem, int B, int n_code, int n_sub, int dim, int dtype,

@@ -192,7 +192,8 @@ def main_train():
                                          # per-commit packed node rows (packed.py) by default; FIRA_LAYOUT=trimmed keeps
                                          # the padded batches cut to the batch maximum
                                          packed=os.environ.get("FIRA_LAYOUT", "packed") == "packed")
-        dp = GraphedTrainStep(model, args.batch_size, lambda ps: Adam(ps, args.lr, fused=True, capturable=True),
+        from fira_icse_b200.optim import FlatAdam
+        dp = GraphedTrainStep(model, args.batch_size, lambda ps: FlatAdam(ps, lr=args.lr, groups=model.flat_groups()),
                               edge_capacity=train_loader.edge_cap)
     else:
         train_loader = loader(train_set, args.batch_size, True, list(range(lo, hi)) if WORLD > 1 else None)
