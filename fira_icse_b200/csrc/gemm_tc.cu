@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <atomic>
+#include <stdlib.h>
 #include "common.cuh"
 #include "fira_b200.h"
 
@@ -33,6 +34,9 @@ struct TcParams {
   int relu; int accumulate;
   int splits; int kblocks_per_split;
   int a_kmajor, b_kmajor;
+  int rotate;                  // CTAs start their k loop at different k-blocks (see the producer)
+  int tma_store;               // bf16 output written by TMA (cp.async.bulk.tensor store) from a swizzled staging tile
+  float* colsum;               // optional (MN-major A only): colsum[m] += sum_k A(m, k) -- the bias gradient of a wgrad product
   unsigned long long* probe;   // debugging aid (fira_debug_set_probe): CTA (0,0,0) stamps %globaltimer at its phase boundaries
 };
 
@@ -97,8 +101,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 //                      panels, SBO = 1024 between 8-k groups); one TMA box per panel.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(16) float s_bias[BN], s_rc[BN];   // per-column epilogue constants of this tile (TMA-store path)
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
@@ -112,12 +118,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nkb = kb_end - kb_begin;
   if (threadIdx.x == 0) stamp(p, 0);                 // kernel entry
 
+  // bias gradient folded into the weight-gradient product: the CTAs of the first column tile also sum the A tile
+  // (= dY^T) over k as it passes through shared memory; a stage is then released by the MMAs AND the four summing warps
+  const bool do_cs = p.colsum != nullptr && blockIdx.x == 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_addr(&full_bar[s]), 1); mbar_init(smem_addr(&empty_bar[s]), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_addr(&full_bar[s]), 1); mbar_init(smem_addr(&empty_bar[s]), do_cs ? 5 : 1); }
     mbar_init(smem_addr(&tmem_full_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_slot)), "r"(BN));
@@ -140,7 +150,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
       const uint32_t fb = smem_addr(&full_bar[s]);
       mbar_expect_tx(fb, STAGE_BYTES);
-      const int k0 = (kb_begin + i) * BK;
+      // The CTAs of one tile row all read the same A tile and those of one tile column the same B tile, at the same
+      // moment: the phase probe showed the load phase growing with the number of CTAs that share a tile (1.1 us with 4
+      // sharers, 5.1 us with 8) -- same-line contention in L2.  Rotating the k-block order by the tile coordinates makes
+      // the sharers ask for different lines at any one time; the fp32 sum over k-blocks is order-independent up to
+      // rounding.
+      const int kb = p.rotate ? kb_begin + (i + (int)(blockIdx.x + blockIdx.y)) % nkb : kb_begin + i;
+      const int k0 = kb * BK;
       if (p.a_kmajor) {
         tma_load_2d(sa, &tmA, k0, m0, fb);                        // box {64 k, 128 m}
       } else {
@@ -195,13 +211,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int LPR = HB / 8;                     // lanes per row on the way out (8 columns per lane)
     constexpr int RPI = 32 / LPR;                   // rows per store iteration
     float* stg = reinterpret_cast<float*>(smem_dyn + (base - smem_addr(smem_dyn))) + (size_t)quarter * 32 * PITCH;
+    if (do_cs) {
+      // thread <-> one of the 128 m columns of the MN-major A tile: [m/64][64 k][64 m] bf16, 128-B rows, SWIZZLE_128B
+      const int t = quarter * 32 + lane;
+      const unsigned char* a_base = smem_dyn + (base - smem_addr(smem_dyn)) + (t >> 6) * 8192 + (t & 7) * 2;
+      const int chunk = (t & 63) >> 3;
+      float cs = 0.f;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(smem_addr(&full_bar[s]), (i / STAGES) & 1);
+        const unsigned char* a = a_base + (size_t)s * STAGE_BYTES;
+#pragma unroll 8
+        for (int k = 0; k < BK; ++k)
+          cs += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(a + (k >> 3) * 1024 + (k & 7) * 128 + ((chunk ^ (k & 7)) << 4)));
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&empty_bar[s])) : "memory");
+      }
+      if (m0 + t < p.M) atomicAdd(p.colsum + m0 + t, cs);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // every summing warp is done with the stages before one is reused for staging
+    }
+    const int mrow0 = m0 + quarter * 32;
+    if (p.tma_store) {                               // per-column constants -> shared memory while the MMAs run
+      for (int c = quarter * 32 + lane; c < BN; c += 128) {
+        const int n = n0 + c;
+        s_bias[c] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+        s_rc[c] = (p.rs && n < p.N) ? p.rc[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     if (nkb > 0) {
       mbar_wait(smem_addr(&tmem_full_bar), 0);
       tc_fence_after();
     }
+    if (p.tma_store) {
+      // ---- bf16 output through TMA: each warp converts its 32 rows, 64 columns at a time, into a [32 x 64] bf16 box in
+      // the SWIZZLE_128B layout (conflict-free 16-byte st.shared: lane = row, chunk slot = chunk ^ (row & 7)) and one
+      // elected lane hands the box to the TMA engine; rows / columns past M / N are clipped by the tensor map.  The
+      // per-column constants were staged in shared memory while the MMAs ran.  (probe: 1.7 us -> for the 128 x 64 tile
+      // of the smem-staged path below, 6.7 us for 128 x 256.)
+      unsigned char* cst = smem_dyn + (base - smem_addr(smem_dyn)) + (size_t)quarter * (BN / 64) * 4096;
+      const int m = mrow0 + lane;
+      const float rsm = (p.rs && m < p.M) ? p.rs[m] : 0.f;
+      if (warp == 2 && lane == 0) stamp(p, 6);
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          const int c0 = g * 64 + h * 32;
+          if (nkb > 0) {
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + q * 8), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + q * 8 + 4);
+            const float4 k0 = *reinterpret_cast<const float4*>(s_rc + c0 + q * 8), k1 = *reinterpret_cast<const float4*>(s_rc + c0 + q * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] = fmaf(rsm, kk[j], __uint_as_float(r[q * 8 + j]) + bb[j]);
+              if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4 o;
+            __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            const int chunk = h * 4 + q;
+            *reinterpret_cast<uint4*>(cst + g * 4096 + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && n0 + g * 64 < p.N && mrow0 < p.M)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&tmC), "r"(smem_addr(cst + g * 4096)), "r"(n0 + g * 64), "r"(mrow0) : "memory");
+      }
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      __syncwarp();
+    } else {
     if (warp == 2 && lane == 0) stamp(p, 6);         // accumulator visible to the epilogue
     const bool first = blockIdx.z == 0;
-    const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1
     for (int hb = 0; hb < BN; hb += HB) {
 #pragma unroll 1
@@ -306,6 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __syncwarp();                                 // staging block free for the next column pass
     }
+    }   // smem-staged epilogue
   }
   if (warp == 2 && lane == 0) stamp(p, 7);           // this warp's stores issued
   tc_fence_before();
@@ -318,6 +425,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- host side
+bool tma_store_on() {          // FIRA_GEMM_TMA_STORE=0: A/B switch back to the register / shared-memory epilogue
+  static const bool on = [] { const char* e = getenv("FIRA_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+bool rotate_on() {             // FIRA_GEMM_ROTATE=0: every CTA walks k in the same order
+  static const bool on = [] { const char* e = getenv("FIRA_GEMM_ROTATE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 PFN_cuTensorMapEncodeTiled get_encode() {
   static PFN_cuTensorMapEncodeTiled fn = [] {
     void* f = nullptr;
@@ -347,13 +464,13 @@ int make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, i
 }
 
 template <int BN, int STAGES>
-int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
   // per launch, not cached in a static: the attribute is per device, and a static flag would be shared state
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_tc attr: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
-  launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(NUM_THREADS), smem, st, ta, tb, p);
+  launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(NUM_THREADS), smem, st, ta, tb, tc, p);
   return FIRA_OK;
 }
 
@@ -363,10 +480,10 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, 
 //   at most one wave   -> 4-stage ring, one CTA per SM: all four k-blocks of a K = 256 product are in flight at
 //                         once, which is what the latency-bound 15-105 CTA launches of the decoder need.
 template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, cudaStream_t st) {
   const long ctas = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
-  if (ctas > 148) return launch_cfg<BN, (BN == 256 ? 2 : 3)>(ta, tb, p, st);
-  return launch_cfg<BN, 4>(ta, tb, p, st);
+  if (ctas > 148) return launch_cfg<BN, (BN == 256 ? 2 : 3)>(ta, tb, tc, p, st);
+  return launch_cfg<BN, 4>(ta, tb, tc, p, st);
 }
 
 }  // namespace
@@ -379,9 +496,10 @@ extern "C" int fira_debug_set_probe(void* probe) {
   return FIRA_OK;
 }
 
-extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
-                                 long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
-                                 const float* rc, int relu, int accumulate, int splits, void* stream) {
+namespace {
+int gemm_tc_impl(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C, long ldc,
+                 int c_is_bf16, int M, int N, int K, const float* bias, const float* rs, const float* rc, int relu,
+                 int accumulate, int splits, float* colsum, void* stream) {
   FIRA_CHECK_ARG(A && B && C, FIRA_ERR_ARG, "gemm_bf16_tc: null operand");
   FIRA_CHECK_ARG(M > 0 && N > 0 && K > 0, FIRA_ERR_SHAPE, "gemm_bf16_tc: M=%d N=%d K=%d", M, N, K);
   FIRA_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, FIRA_ERR_ALIGN, "gemm_bf16_tc: lda/ldb must be multiples of 8");
@@ -411,16 +529,44 @@ extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const vo
   if (splits > kb_total) splits = kb_total;
   int per = (kb_total + splits - 1) / splits;
   splits = (kb_total + per - 1) / per;
-  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits, per, a_kmajor, b_kmajor,
+  // bf16 output that is neither accumulated nor split: written by TMA from a swizzled staging tile ([32 rows x 64
+  // columns] boxes); everything else takes the register / shared-memory epilogue
+  const int tma_store = (c_is_bf16 && !accumulate && splits == 1 && (ldc % 8) == 0 && tma_store_on()) ? 1 : 0;
+  CUtensorMap tc = ta;
+  if (tma_store) {
+    rc_ = make_map(&tc, C, M, N, ldc, 64, 32);
+    if (rc_) return rc_;
+  }
+  TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits, per, a_kmajor, b_kmajor, rotate_on() ? 1 : 0,
+             tma_store, colsum,
              g_probe.load(std::memory_order_relaxed)};
   if (splits > 1 && !accumulate) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
     if (e != cudaSuccess) { fira_set_error(FIRA_ERR_CUDA, "gemm_bf16_tc memset: %s", cudaGetErrorString(e)); return FIRA_ERR_CUDA; }
   }
-  if (BN == 256) rc_ = launch<256>(ta, tb, p, st);
-  else if (BN == 128) rc_ = launch<128>(ta, tb, p, st);
-  else rc_ = launch<64>(ta, tb, p, st);
+  if (BN == 256) rc_ = launch<256>(ta, tb, tc, p, st);
+  else if (BN == 128) rc_ = launch<128>(ta, tb, tc, p, st);
+  else rc_ = launch<64>(ta, tb, tc, p, st);
   if (rc_) return rc_;
   FIRA_CHECK_LAUNCH("fira_gemm_bf16_tc");
   return FIRA_OK;
+}
+}  // namespace
+
+extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C,
+                                 long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
+                                 const float* rc, int relu, int accumulate, int splits, void* stream) {
+  return gemm_tc_impl(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits,
+                      nullptr, stream);
+}
+
+// Weight-gradient product with the bias gradient folded in: C[M,N] = A^T-stored (MN-major) A times B as above, and
+// d_bias[m] += sum_k A(m, k) (atomic accumulation into a zero-filled buffer), read from the A tiles as they pass through
+// shared memory -- the separate column-sum pass over dY disappears.
+extern "C" int fira_gemm_bf16_tc_dbias(const void* A, long lda, const void* B, long ldb, int b_kmajor, void* C, long ldc,
+                                       int c_is_bf16, int M, int N, int K, int accumulate, int splits, float* d_bias,
+                                       void* stream) {
+  FIRA_CHECK_ARG(d_bias != nullptr, FIRA_ERR_ARG, "gemm_bf16_tc_dbias: null d_bias");
+  return gemm_tc_impl(A, lda, 0, B, ldb, b_kmajor, C, ldc, c_is_bf16, M, N, K, nullptr, nullptr, nullptr, 0, accumulate,
+                      splits, d_bias, stream);
 }

@@ -136,6 +136,15 @@ class GraphedTrainStep:
         if self.flat_optims:
             _optim.attach(self.model, self.flat_optims)
 
+    def _cap_stream(self):
+        """Capture stream of the step graphs: HIGH priority, so that the kernels of the main chain (the critical path:
+        forward, input gradients) carry a higher launch priority than the weight-gradient / preparation work on the
+        default-priority side streams that runs next to them (FIRA_MAIN_PRIORITY=0: default priority)."""
+        if getattr(self, "_cap_s", None) is None:
+            hi = os.environ.get("FIRA_MAIN_PRIORITY", "1") != "0"
+            self._cap_s = torch.cuda.Stream(priority=-1) if hi else torch.cuda.Stream()
+        return self._cap_s
+
     def _zero(self):
         self.bucket.zero()
         for o in self.flat_optims:
@@ -245,7 +254,7 @@ class GraphedTrainStep:
     def _capture_split(self, c):
         flat = bool(self.flat_optims)
         c.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(c.graph, pool=self.pool):
+        with torch.cuda.graph(c.graph, pool=self.pool, stream=self._cap_stream()):
             self._phase_a(c)
         if self.params_a is None:
             self.params_a = [p for p in self.bucket.params if p.grad is not None]
@@ -253,7 +262,7 @@ class GraphedTrainStep:
             self.params_b = [p for p in self.bucket.params if id(p) not in ids]
         c.grads_a = [p.grad for p in self.params_a]
         c.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(c.graph_b, pool=self.pool):
+        with torch.cuda.graph(c.graph_b, pool=self.pool, stream=self._cap_stream()):
             self._phase_b()
         c.grads_b = [p.grad for p in self.params_b]
         assert all(g is not None for g in c.grads_a + c.grads_b), "a live parameter received no gradient"
@@ -373,7 +382,7 @@ class GraphedTrainStep:
         if self.split:
             return self._capture_split(c)
         c.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(c.graph, pool=self.pool):
+        with torch.cuda.graph(c.graph, pool=self.pool, stream=self._cap_stream()):
             if self.world == 1 and self.opt_overlap:
                 # ONE graph, two branches: Adam on the head/decoder parameters (3/4 of the bytes, memory-bound, nothing
                 # else could hide it at the end of the step) runs on a side stream WHILE the encoder backward runs

@@ -187,12 +187,22 @@ class Prec:
         return gemm_tc(dy, ld_dy, 1, self.w(W), K, 0, out, K, M, K, N, accumulate=accumulate, a_off=dy_off)
 
     # dW = dy^T x   (fp32 result in both modes)
-    def linear_dw(self, dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0, out=None):
+    def linear_dw(self, dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0, out=None, dbias=None):
+        """dW = dy^T x.  dbias: zero-filled fp32 [N] that receives the bias gradient colsum(dy) -- in bf16 mode from the
+        same launch (fira_gemm_bf16_tc_dbias sums the dy tiles in shared memory), in fp32 mode from fira_colsum."""
         if not self.bf16:
+            if dbias is not None:
+                colsum(dy, ld_dy, M, N, x_off=dy_off, out=dbias)
             return linear_dw(dy, ld_dy, x, ldx, M, N, K, dy_off=dy_off, x_off=x_off, out=out)
         dW = torch.empty((N, K), dtype=torch.float32, device=dy.device) if out is None else out
         bn = 256 if K > 128 else (128 if K > 64 else 64)
         splits = _tc_splits(_ceil(N, 128) * _ceil(K, bn), _ceil(M, 64))
+        if dbias is not None and os.environ.get("FIRA_DBIAS_FUSED", "1") != "0":
+            call("fira_gemm_bf16_tc_dbias", _ptr(dy, dy_off), ld_dy, _ptr(x, x_off), ldx, 0, _ptr(dW), K, 0, N, K, M, 0, splits,
+                 _ptr(dbias), _stream())
+            return dW
+        if dbias is not None:
+            colsum(dy, ld_dy, M, N, x_off=dy_off, out=dbias)
         return gemm_tc(dy, ld_dy, 0, x, ldx, 0, dW, K, N, K, M, splits=splits, a_off=dy_off, b_off=x_off)
 
     def ln_fwd(self, z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid):
@@ -481,14 +491,15 @@ class EncoderFn(torch.autograd.Function):
                 call("fira_gcn_layer_bwd", _ptr(etrows[0]), _ptr(etrows[1]), _ptr(etrows[2]), _ptr(dZ), _ptr(WcT16),
                      _ptr(dRes), _ptr(AdZ), _ptr(dGin_i), R, D, st)
             with fork(dZ, G, rs, W1, W2, b1):
-                d_b2 = colsum(dZ, D, R, D, out=_gdest(b2, (D,), zero=True))
+                d_b2 = _gdest(b2, (D,), zero=True)
                 if fused:                       # dZ^T (A H) = (A^T dZ)^T H ;  sum_i rowsum(A)_i dZ_i = colsum(A^T dZ)
                     fork.keep.append(AdZ)
-                    d_c1 = colsum(AdZ, D, R, D)
-                    dWc = pr.linear_dw(AdZ, D, Gin, D, R, D, D)
+                    colsum(dZ, D, R, D, out=d_b2)
+                    d_c1 = torch.zeros(D, dtype=torch.float32, device=dev)
+                    dWc = pr.linear_dw(AdZ, D, Gin, D, R, D, D, dbias=d_c1)
                 else:
                     d_c1 = colsum(dZ, D, R, D, weight=rs)
-                    dWc = pr.linear_dw(dZ, D, G, D, R, D, D)
+                    dWc = pr.linear_dw(dZ, D, G, D, R, D, D, dbias=d_b2)
                 d_W2 = _gdest(W2, (D, D))               # dWc W1^T + d_c1 b1^T
                 gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=MERGE_SPLITS if pr.bf16 else 1)
                 d_W1 = _gdest(W1, (D, D))               # W2^T dWc
@@ -505,16 +516,16 @@ class EncoderFn(torch.autograd.Function):
             dZc, _, d_clw, d_clb = pr.ln_bwd(dGin_i, dGin_i, Mc, Zc, Xc, st_c, clw, Mc, p_comb, seed, sid + 1,
                                              d_resid=dXc_n, beta=clb)
             with fork(dZc, Cd):
-                d_bo = colsum(dZc, D, Mc, D, out=_gdest(bo, (D,), zero=True))
-                d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D, out=_gdest(Wo, (D, D)))
+                d_bo = _gdest(bo, (D,), zero=True)
+                d_Wo = pr.linear_dw(dZc, D, Cd, D, Mc, D, D, out=_gdest(Wo, (D, D)), dbias=d_bo)
             dCd = pr.linear_dx(dZc, D, Wo, Mc)
             dQK = pr.empty((Mc, 2 * D), dev)
             dVtab = torch.zeros((4, D), **f32)
             call("fira_comb_gate_bwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(dCd), _ptr(dQK), _ptr(dVtab),
                  Mc, D, D // heads, float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
             with fork(dQK, Xc, dVtab, mark_emb, Wv, d_mark_emb, lane=0):     # d_mark_emb accumulates across layers
-                d_bqk = colsum(dQK, 2 * D, Mc, 2 * D, out=_gdest((bq, bk), (2 * D,), zero=True))
-                d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D, out=_gdest((Wq, Wk), (2 * D, D)))
+                d_bqk = _gdest((bq, bk), (2 * D,), zero=True)
+                d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D, out=_gdest((Wq, Wk), (2 * D, D)), dbias=d_bqk)
                 d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D, out=_gdest(Wv, (D, D)))
                 d_bv = colsum(dVtab, D, 4, D, out=_gdest(bv, (D,), zero=True))
                 linear_dx(dVtab, D, Wv, 4, out=d_mark_emb, accumulate=True)
@@ -639,19 +650,19 @@ class DecoderFn(torch.autograd.Function):
             # ---- FFN
             dZ3, dX2, d_flw, d_flb = pr.ln_bwd(dX, dX, Mt, Z3, X2, ls3, flw, Mt, p, seed, sid + 2, beta=flb)
             with fork(dZ3, Hh):
-                d_fb2 = colsum(dZ3, D, Mt, D, out=_gdest(fb2, (D,), zero=True))
-                d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F, out=_gdest(fW2, (D, F)))
+                d_fb2 = _gdest(fb2, (D,), zero=True)
+                d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F, out=_gdest(fW2, (D, F)), dbias=d_fb2)
             dHh = pr.linear_dx(dZ3, D, fW2, Mt)                           # [Mt, 1024]
             call("fira_relu_bwd", _ptr(Hh), _ptr(dHh), Mt * F, pr.code, st)
             with fork(dHh, X2):
-                d_fb1 = colsum(dHh, F, Mt, F, out=_gdest(fb1, (F,), zero=True))
-                d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D, out=_gdest(fW1, (F, D)))
+                d_fb1 = _gdest(fb1, (F,), zero=True)
+                d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D, out=_gdest(fW1, (F, D)), dbias=d_fb1)
             pr.linear_dx(dHh, F, fW1, Mt, out=dX2, accumulate=True)
             # ---- cross-attention
             dZ2, dX1, d_clw, d_clb = pr.ln_bwd(dX2, dX2, Mt, Z2, X1, ls2, clw, Mt, p, seed, sid + 1, beta=clb)
             with fork(dZ2, ctx2):
-                d_cbo = colsum(dZ2, D, Mt, D, out=_gdest(cbo, (D,), zero=True))
-                d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D, out=_gdest(cWo, (D, D)))
+                d_cbo = _gdest(cbo, (D,), zero=True)
+                d_cWo = pr.linear_dw(dZ2, D, ctx2, D, Mt, D, D, out=_gdest(cWo, (D, D)), dbias=d_cbo)
             dctx2 = pr.linear_dx(dZ2, D, cWo, Mt)
             dQ = pr.empty((Mt, D), dev)
             if pk is not None:
@@ -663,22 +674,22 @@ class DecoderFn(torch.autograd.Function):
                      _ptr(mem_mask), 0, _ptr(ctx2), _ptr(dctx2), D, _ptr(st2), _ptr(dQ), D, _ptr(dKV, i * 2 * D), ldkv,
                      _ptr(dKV, i * 2 * D + D), ldkv, B, H, T, S, D // H, pr.code, st)
             with fork(dQ, X1):
-                d_cbq = colsum(dQ, D, Mt, D, out=_gdest(cbq, (D,), zero=True))
-                d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D, out=_gdest(cWq, (D, D)))
+                d_cbq = _gdest(cbq, (D,), zero=True)
+                d_cWq = pr.linear_dw(dQ, D, X1, D, Mt, D, D, out=_gdest(cWq, (D, D)), dbias=d_cbq)
             pr.linear_dx(dQ, D, cWq, Mt, out=dX1, accumulate=True)
             # ---- self-attention
             dZ1, dX0, d_slw, d_slb = pr.ln_bwd(dX1, dX1, Mt, Z1, X, ls1, slw, Mt, p, seed, sid + 0, beta=slb)
             with fork(dZ1, ctx1):
-                d_sbo = colsum(dZ1, D, Mt, D, out=_gdest(sbo, (D,), zero=True))
-                d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D, out=_gdest(sWo, (D, D)))
+                d_sbo = _gdest(sbo, (D,), zero=True)
+                d_sWo = pr.linear_dw(dZ1, D, ctx1, D, Mt, D, D, out=_gdest(sWo, (D, D)), dbias=d_sbo)
             dctx1 = pr.linear_dx(dZ1, D, sWo, Mt)
             dQKV = pr.empty((Mt, 3 * D), dev)
             call("fira_attn_bwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
                  _ptr(ctx1), _ptr(dctx1), D, _ptr(st1), _ptr(dQKV), 3 * D, _ptr(dQKV, D), 3 * D, _ptr(dQKV, 2 * D), 3 * D,
                  B, H, T, T, D // H, pr.code, st)
             with fork(dQKV, X):
-                d_bqkv = colsum(dQKV, 3 * D, Mt, 3 * D, out=_gdest((sbq, sbk, sbv), (3 * D,), zero=True))
-                d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D, out=_gdest((sWq, sWk, sWv), (3 * D, D)))
+                d_bqkv = _gdest((sbq, sbk, sbv), (3 * D,), zero=True)
+                d_Wqkv = pr.linear_dw(dQKV, 3 * D, X, D, Mt, 3 * D, D, out=_gdest((sWq, sWk, sWv), (3 * D, D)), dbias=d_bqkv)
             pr.linear_dx(dQKV, 3 * D, Wqkv, Mt, out=dX0, accumulate=True)
             grads[i * 26:(i + 1) * 26] = [
                 d_Wqkv[:D], d_bqkv[:D], d_Wqkv[D:2 * D], d_bqkv[D:2 * D], d_Wqkv[2 * D:], d_bqkv[2 * D:],
@@ -692,8 +703,8 @@ class DecoderFn(torch.autograd.Function):
         with fork(dKV, mem2):
             kv_w = [t for i in range(L) for t in (lp[i * 26 + 12], lp[i * 26 + 14])]
             kv_b = [t for i in range(L) for t in (lp[i * 26 + 13], lp[i * 26 + 15])]
-            d_bkv = colsum(dKV, ldkv, Ms, ldkv, out=_gdest(kv_b, (ldkv,), zero=True))
-            d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D, out=_gdest(kv_w, (ldkv, D)))
+            d_bkv = _gdest(kv_b, (ldkv,), zero=True)
+            d_Wkv = pr.linear_dw(dKV, ldkv, mem2, D, Ms, ldkv, D, out=_gdest(kv_w, (ldkv, D)), dbias=d_bkv)
         d_mem = pr.linear_dx(dKV, ldkv, Wkv, Ms).view(memory.shape).to(mem_dtype)
         for i in range(L):
             o = i * 2 * D
@@ -801,8 +812,8 @@ class HeadFn(torch.autograd.Function):
         fork = Fork(dev)
         with fork(d_src, memory2, dlogits, dec2, dgl, dec32, d_tgt):
             d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D, out=_gdest(Ws, (D, D)))
-            d_bout = colsum(dlogits, ldl, Mt, V, out=_gdest(bout, (V,), zero=True))
-            d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D, out=_gdest(Wout, (V, D)))
+            d_bout = _gdest(bout, (V,), zero=True)
+            d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D, out=_gdest(Wout, (V, D)), dbias=d_bout)
             d_bp = colsum(dgl, 2, Mt, 2, out=_gdest(bp, (2,), zero=True))
             d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D, out=_gdest(Wp, (2, D)))
             d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D, out=_gdest(Wt, (D, D)))

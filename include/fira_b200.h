@@ -66,6 +66,13 @@ int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const void* B, long
                       long ldc, int c_is_bf16, int M, int N, int K, const float* bias, const float* rs,
                       const float* rc, int relu, int accumulate, int splits, void* stream);
 
+/* Weight-gradient form with the bias gradient folded in (every `dW = dY^T X`, `db = colsum(dY)` pair of the backward
+ * pass, e.g. gnn_transformer.py:141-143,158,171-173 under autograd): A = dY read MN-major (A(m,k) = A[k*lda+m]),
+ * C[M,N] = A B as above, and d_bias[m] += sum_k A(m,k), accumulated atomically into a zero-filled buffer from the A
+ * tiles while they sit in shared memory -- no separate column-sum pass over dY. */
+int fira_gemm_bf16_tc_dbias(const void* A, long lda, const void* B, long ldb, int b_kmajor, void* C, long ldc,
+                            int c_is_bf16, int M, int N, int K, int accumulate, int splits, float* d_bias, void* stream);
+
 /* Debugging aid (tools/gemm_probe.py): with a device buffer of >= 16 uint64 set, CTA (0,0,0) of every following
  * fira_gemm_bf16_tc launch stamps %globaltimer at its phase boundaries (entry, prologue, dependency wait, TMA issued,
  * first stage landed, MMAs issued, accumulator ready, stores issued, exit); NULL switches it off (the default). */

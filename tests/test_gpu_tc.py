@@ -73,3 +73,21 @@ def test_mnmajor_weight_grad_and_input_grad(rows, N, K):
     dx = torch.empty((rows, K), device=DEV, dtype=torch.bfloat16)
     o.gemm_tc(dy, N, 1, W, K, 0, dx, K, rows, K, N)
     close(dx.float(), dy.float() @ W.float(), rtol=1e-2)
+
+
+@pytest.mark.parametrize("rows,N,K,ld", [(1000, 256, 256, 256), (1920, 1024, 256, 1024), (333, 72, 136, 72), (1920, 768, 256, 768),
+                                         (1920, 24650, 256, 24704), (11000, 3072, 256, 3072), (77, 256, 1024, 256)])
+def test_weight_grad_with_folded_bias_grad(rows, N, K, ld):
+    """fira_gemm_bf16_tc_dbias: dW = dY^T X and db += colsum(dY) from the same launch (dY tiles summed in shared memory)"""
+    from fira_icse_b200 import ops as o
+    dy = torch.zeros((rows, ld), device=DEV, dtype=torch.bfloat16)
+    dy[:, :N] = rnd(rows, N, seed=1)
+    x = rnd(rows, K, seed=2)
+    pr = o.Prec(True)
+    ref_w, ref_b = dy[:, :N].float().T @ x.float(), dy[:, :N].float().sum(0)
+    for _ in range(2):                                   # the second pass checks nothing is left behind in the buffers
+        dW = torch.full((N, K), 7.0, device=DEV)
+        db = torch.zeros(N, device=DEV)
+        pr.linear_dw(dy, ld, x, K, rows, N, K, out=dW, dbias=db)
+        close(dW, ref_w)
+        close(db, ref_b)
