@@ -196,9 +196,47 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-def spmm_roofline(dev, hb, B, bf16=False):
-    """Time fira_gcn_aggregate alone (CUDA events on the launching stream), cold L2: the launches rotate
-    through buffer pairs whose total size exceeds the 126 MB L2."""
+def time_launches(launch, n_rot, reps=None, iters=12):
+    """Average device time of ONE launch of a kernel, measured live: `reps` launches over `n_rot` rotating buffer sets
+    (total > L2, so every launch finds its operands in HBM) are captured into one CUDA graph -- the way the training step
+    issues them -- and the graph is replayed `iters` times between CUDA events recorded on the replay stream.  Launching
+    one kernel at a time from Python would time the host's launch latency instead (the kernels here run 5-40 us)."""
+    import torch
+    reps = reps or max(8, n_rot)
+    reps = (reps + n_rot - 1) // n_rot * n_rot
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for i in range(n_rot):
+            launch(i)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(reps):
+            launch(i)
+    g.replay()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record()
+        g.replay()
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) / reps for a, b in ev)
+    return sum(ms) / len(ms), ms[len(ms) // 2], reps * iters
+
+
+def _cur():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+TIMING_NOTE = "launches replayed from one CUDA graph over rotating buffer sets, CUDA events around the replay"
+
+
+def spmm_roofline(dev, hb, B, bf16=False, label=None):
+    """fira_gcn_aggregate (the stand-alone GNN scatter) on the padded 650-row graphs of `hb` (B commits), cold L2."""
     import torch
     from fira_icse_b200 import _lib
     from fira_icse_b200.graph import PackedEdges
@@ -206,53 +244,65 @@ def spmm_roofline(dev, hb, B, bf16=False):
     _, (rowptr, col, val), _ = hb
     pe = PackedEdges.from_host(rowptr, col, val, B, N_NODES, dev)
     R = B * N_NODES
-    n_pairs = max(3, int(400e6 // (2 * R * 256 * 4)) + 1)
     tdt, esz, code = (torch.bfloat16, 2, 1) if bf16 else (torch.float32, 4, 0)
     n_pairs = max(3, int(400e6 // (2 * R * 256 * esz)) + 1)
     xs = [torch.randn(R, 256, device=dev).to(tdt) for _ in range(n_pairs)]
     ys = [torch.empty(R, 256, device=dev, dtype=tdt) for _ in range(n_pairs)]
-    st = torch.cuda.current_stream()
 
     def launch(i):
         _lib.call("fira_gcn_aggregate", pe.rowptr.data_ptr(), pe.col.data_ptr(), pe.val.data_ptr(),
-                  xs[i % n_pairs].data_ptr(), None, ys[i % n_pairs].data_ptr(), B, N_CODE, N_SUB, N_AST, 256, code,
-                  st.cuda_stream)
-    for i in range(6):
-        launch(i)
-    iters = 40
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    torch.cuda.synchronize()
-    for i in range(iters):
-        ev[i][0].record(st)
-        launch(i)
-        ev[i][1].record(st)
-    torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    avg_ms = sum(ms) / len(ms)
+                  xs[i % n_pairs].data_ptr(), None, ys[i % n_pairs].data_ptr(), B, N_CODE, N_SUB, N_AST, 256, code, _cur())
+    avg_ms, med_ms, n = time_launches(launch, n_pairs)
     alg_bytes = 2 * R * 256 * esz + (R + 1) * 4 + pe.nnz * 8        # SURVEY.md section 8d formula
     peak, how = measured_peaks()
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu captures
+    if os.path.exists(tpath) and B == PER_GPU_BATCH:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu)
         traffic = json.load(open(tpath)).get("fira_gcn_aggregate_bf16_dram_bytes_per_launch" if bf16 else
                                              "fira_gcn_aggregate_dram_bytes_per_launch")
     kname = "csr_spmm_part_kernel<bf16,16>" if bf16 else "csr_spmm_kernel<float>"
+    del xs, ys
     return {"bound": "hbm", "kernel": kname + " (fira_gcn_aggregate, the GNN scatter)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "median_launch_ms": ms[len(ms) // 2],
-            "launches_timed": iters, "rows": R, "nnz": pe.nnz, "peak_source": how,
-            "dtype": "bf16" if bf16 else "f32",
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "median_launch_ms": med_ms,
+            "launches_timed": n, "rows": R, "nnz": pe.nnz, "commits": B, "peak_source": how,
+            "dtype": "bf16" if bf16 else "f32", "shape": label or f"{B} commits x 650 padded node rows",
+            "timing": TIMING_NOTE,
             "l2": f"cold: {n_pairs} rotating buffer pairs ({n_pairs * 2 * R * 256 * esz / 1e6:.0f} MB > 126 MB L2)"}
+
+
+def spmm_packed_roofline(dev, pb):
+    """The same kernel on the rows the TIMED STEP launches it on: the per-commit packed node rows of one bench batch
+    (B = 1 ragged graph).  ~11 k rows = 12 MB: far too small for the HBM roofline to be the bound (launch + latency)."""
+    import torch
+    from fira_icse_b200 import _lib
+    R = pb.rows
+    n_pairs = max(3, int(400e6 // (2 * R * 256 * 2)) + 1)
+    xs = [torch.randn(R, 256, device=dev).to(torch.bfloat16) for _ in range(n_pairs)]
+    ys = [torch.empty(R, 256, device=dev, dtype=torch.bfloat16) for _ in range(n_pairs)]
+
+    def launch(i):
+        _lib.call("fira_gcn_aggregate", pb.rowptr.data_ptr(), pb.col.data_ptr(), pb.val.data_ptr(),
+                  xs[i % n_pairs].data_ptr(), None, ys[i % n_pairs].data_ptr(), 1, pb.Rc, pb.Rs, pb.Ra, 256, 1, _cur())
+    avg_ms, med_ms, n = time_launches(launch, n_pairs, reps=2 * n_pairs)
+    nnz = int(pb.nnz)
+    alg_bytes = 2 * R * 256 * 2 + (R + 1) * 4 + nnz * 8
+    peak, how = measured_peaks()
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "csr_spmm_part_kernel<bf16,16> (fira_gcn_aggregate) on the packed rows of the timed step",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "median_launch_ms": med_ms,
+            "launches_timed": n, "rows": R, "nnz": nnz, "peak_source": how, "dtype": "bf16", "timing": TIMING_NOTE,
+            "note": "12 MB per launch: a same-size device copy does not reach the HBM roofline either; latency-bound"}
 
 
 # ------------------------------------------------------------------------------------------------ fused GCN roofline
 def gcn_fused_roofline(dev, pb):
     """The fused GCN layer kernel (fira_gcn_layer_fwd: gather -> tcgen05 -> bias/rowsum/dropout/residual/LayerNorm out of
-    TMEM, ONE launch) timed alone with CUDA events on the node rows / adjacency of a packed bench batch `pb` (device),
-    cold L2 (rotating buffer sets larger than the 126 MB L2).  Algorithmic bytes = SURVEY.md 8d's fused formula: read H
-    once + write the layer output once + rowptr + (col, val) + the weight once per launch; the kernel also writes Z (the
-    pre-LayerNorm rows the backward needs) -- reported separately, not counted as algorithmic."""
+    TMEM, ONE launch) on the node rows / adjacency of a packed bench batch `pb` (device), cold L2.  Algorithmic bytes =
+    SURVEY.md 8d's fused formula: read H once + write the layer output once + rowptr + (col, val) + the weight once per
+    launch; the kernel also writes Z (the pre-LayerNorm rows the backward needs) -- reported separately."""
     import torch
     from fira_icse_b200 import _lib
     R, Mc = pb.rows, pb.Rc
@@ -266,26 +316,14 @@ def gcn_fused_roofline(dev, pb):
     b2, c1 = torch.randn(256, device=dev) * 0.1, torch.randn(256, device=dev) * 0.1
     gamma, beta = torch.ones(256, device=dev), torch.zeros(256, device=dev)
     stats = torch.empty(2, R, device=dev)
-    st = torch.cuda.current_stream()
 
     def launch(i):
         k = i % n_sets
         _lib.call("fira_gcn_layer_fwd", pb.rowptr.data_ptr(), pb.col.data_ptr(), pb.val.data_ptr(), hs[k].data_ptr(),
                   W.data_ptr(), b2.data_ptr(), c1.data_ptr(), gamma.data_ptr(), beta.data_ptr(), zs[k].data_ptr(),
                   oa[k].data_ptr(), ob[k].data_ptr(), Mc, stats.data_ptr(), stats.data_ptr() + 4 * R, R, 256, 0.2, 1234, None,
-                  2, st.cuda_stream)
-    for i in range(6):
-        launch(i)
-    iters = 40
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    torch.cuda.synchronize()
-    for i in range(iters):
-        ev[i][0].record(st)
-        launch(i)
-        ev[i][1].record(st)
-    torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    avg_ms = sum(ms) / len(ms)
+                  2, _cur())
+    avg_ms, med_ms, n = time_launches(launch, n_sets, reps=2 * n_sets)
     nnz = int(pb.nnz)
     alg_bytes = 2 * R * 256 * 2 + (R + 1) * 4 + nnz * 8 + 256 * 256 * 2
     peak, how = measured_peaks()
@@ -297,39 +335,28 @@ def gcn_fused_roofline(dev, pb):
     return {"bound": "hbm", "kernel": "gcn_fused_kernel<0> (fira_gcn_layer_fwd: gather -> tcgen05.mma -> LayerNorm epilogue)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": alg_bytes, "bytes_incl_saved_z": alg_bytes + R * 256 * 2,
-            "avg_launch_ms": avg_ms, "median_launch_ms": ms[len(ms) // 2], "launches_timed": iters, "rows": R, "nnz": nnz,
-            "peak_source": how, "dtype": "bf16",
+            "avg_launch_ms": avg_ms, "median_launch_ms": med_ms, "launches_timed": n, "rows": R, "nnz": nnz,
+            "peak_source": how, "dtype": "bf16", "timing": TIMING_NOTE,
             "shape": "node rows / adjacency of one packed bench batch (per-commit packed layout)",
-            "l2": f"cold: {n_sets} rotating buffer sets ({n_sets * 4 * R * 256 * 2 / 1e6:.0f} MB > 126 MB L2)",
-            "note": "timed with events around one launch from Python: includes the launch gap (~2-3 us at this size)"}
+            "l2": f"cold: {n_sets} rotating buffer sets ({n_sets * 4 * R * 256 * 2 / 1e6:.0f} MB > 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------------------ GEMM roofline
-def gemm_roofline(dev, B):
-    """The kernel with the largest share of the bf16 step is the tcgen05 GEMM; time its most frequent large
-    shape live (the GCN layer product: [B*650, 256] x [256, 256]^T, bf16 in/out) with CUDA events on rotating
-    buffers (> L2) and report it against BOTH measured peaks (it is HBM-bound by arithmetic intensity)."""
+def gemm_roofline(dev, M, N=256, K=256, what="GCN layer product of a padded batch"):
+    """The kernel family with the largest share of the bf16 step is the tcgen05 GEMM: time one shape live (bf16 in /
+    out, bias) on rotating buffers (> L2) and report it against BOTH measured peaks (N = K = 256: HBM-bound by
+    arithmetic intensity)."""
     import torch
     from fira_icse_b200 import ops
-    M, N, K = B * 650, 256, 256
-    n_buf = max(3, int(400e6 // (2 * M * 256 * 2)) + 1)
+    n_buf = max(3, int(400e6 // ((M * K + M * N) * 2)) + 1)
     xs = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(n_buf)]
     ys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(n_buf)]
     W = torch.randn(N, K, device=dev).to(torch.bfloat16)
     bias = torch.randn(N, device=dev)
-    st = torch.cuda.current_stream()
-    for i in range(6):
+
+    def launch(i):
         ops.gemm_tc(xs[i % n_buf], K, 1, W, K, 1, ys[i % n_buf], N, M, N, K, bias=bias)
-    iters = 40
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    torch.cuda.synchronize()
-    for i in range(iters):
-        ev[i][0].record(st)
-        ops.gemm_tc(xs[i % n_buf], K, 1, W, K, 1, ys[i % n_buf], N, M, N, K, bias=bias)
-        ev[i][1].record(st)
-    torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    avg = sum(ms) / len(ms)
+    avg, med, n = time_launches(launch, n_buf, reps=2 * n_buf)
     alg_bytes = (M * K + N * K + M * N) * 2 + N * 4
     flops = 2.0 * M * N * K
     hbm, how = measured_peaks()
@@ -339,13 +366,13 @@ def gemm_roofline(dev, B):
         tf_peak = float(json.load(open(path)).get("bf16_tflops", tf_peak))
     gbs = alg_bytes / (avg * 1e-3) / 1e9
     tfs = flops / (avg * 1e-3) / 1e12
-    return {"kernel": "gemm_tc_kernel<256> (fira_gemm_bf16_tc), GCN layer product", "shape": [M, N, K],
+    del xs, ys
+    return {"kernel": "gemm_tc_kernel (fira_gemm_bf16_tc): " + what, "shape": [M, N, K],
             "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
             "achieved_tflops": tfs, "peak_tflops": tf_peak, "frac_tensor": tfs / tf_peak,
             "algorithmic_bytes_per_launch": alg_bytes, "flops_per_launch": flops, "avg_launch_ms": avg,
-            "launches_timed": iters, "peak_source": how,
-            "note": "arithmetic intensity 2*256/(2+2+~0) ~ 128 FLOP/B < ridge ~250: HBM roofline applies; the launch is "
-                    "latency-bound (K = 256 = four k-blocks per tile), see profiles/gemm_tc_r1_ncu_details.txt"}
+            "median_launch_ms": med, "launches_timed": n, "peak_source": how, "timing": TIMING_NOTE,
+            "note": "arithmetic intensity 2*256/(2+2+~0) ~ 128 FLOP/B < ridge ~250: the HBM roofline applies"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -586,24 +613,32 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
+    # ---- rooflines (CUDA events, launches replayed from a graph over rotating > L2 buffers).  `roofline` = the GNN scatter
+    # (the kernel BASELINE.json's metric names) on the 650-row padded graphs of one 64-commit batch; the same kernel on
+    # the packed rows the timed step really launches it on, and on a batch large enough for HBM to be the bound (512
+    # commits), sit next to it, with the fused GCN layer kernel, the fp32 scatter and the dominant GEMM shapes.
     roof = spmm_roofline(dev, full_host, B, bf16=args.precision == "bf16")
-    roof_f32 = spmm_roofline(dev, full_host, B, bf16=False) if args.precision == "bf16" else None
-    roof_gemm = gemm_roofline(dev, B) if args.precision == "bf16" else None
-    roof_fused = None
+    extra = {}
     if args.precision == "bf16":
-        if packed:
-            roof_fused = gcn_fused_roofline(dev, pool_dev[0])
-        else:
+        torch.cuda.empty_cache()
+        big = 8 * B
+        extra["roofline_scatter_512_commits"] = spmm_roofline(dev, host_batch(0, big, pin=False, trim=False), big, bf16=True)
+        torch.cuda.empty_cache()
+        extra["roofline_scatter_fp32"] = spmm_roofline(dev, full_host, B, bf16=False)
+        pb0 = pool_dev[0] if packed else None
+        if pb0 is None:
             from fira_icse_b200.packed import PackedTables, pack_from_dataset
             from fira_icse_b200.synth import SynthDataset
             import numpy as np
-            roof_fused = gcn_fused_roofline(dev, pack_from_dataset(
-                PackedTables(SynthDataset(rank * N_POOL * B, B, VOCAB, AST_VOCAB)), np.arange(B), VOCAB).to(dev))
+            pb0 = pack_from_dataset(PackedTables(SynthDataset(rank * N_POOL * B, B, VOCAB, AST_VOCAB)), np.arange(B), VOCAB).to(dev)
+        extra["roofline_scatter_step_shape"] = spmm_packed_roofline(dev, pb0)
+        extra["roofline_gcn_fused"] = gcn_fused_roofline(dev, pb0)
+        extra["roofline_gemm"] = gemm_roofline(dev, B * 650)
+        extra["roofline_gemm_decoder"] = gemm_roofline(dev, B * 30, 256, 256, what="decoder projection of the timed step")
+        torch.cuda.empty_cache()
         if os.environ.get("FIRA_GCN_FUSED", "0") != "0":
-            # the GNN message passing of the timed step IS this kernel: it is the headline roofline then
-            roof, roof_scatter_bf16 = roof_fused, roof
-        else:
-            roof_scatter_bf16 = None
+            # the GNN message passing of the timed step IS the fused kernel: it is the headline roofline then
+            roof, extra["roofline_scatter_bf16"] = extra["roofline_gcn_fused"], roof
 
     # ---- CPU baseline on this box's host cores: the unmodified reference, same batch (bounded sample)
     cpu_info = None
@@ -643,8 +678,7 @@ def run_gpu_arm(args):
                             if args.graph else "DataParallelStep.step: TransModel.forward eager + backward + Adam")},
             "e2e_loader": loader_info,
             "e2e_dense_edge": dense_info,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_scatter_fp32": roof_f32,
-            "roofline_gemm": roof_gemm, "roofline_gcn_fused": roof_fused,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, **extra,
             "fp32_parity_mode": parity_info,
             "cpu_baseline": cpu_info, "last_loss": last_loss[0]}
     print(json.dumps(line), flush=True)

@@ -36,6 +36,7 @@ struct TcParams {
   int a_kmajor, b_kmajor;
   int rotate;                  // CTAs start their k loop at different k-blocks (see the producer)
   int tma_store;               // bf16 output written by TMA (cp.async.bulk.tensor store) from a swizzled staging tile
+  const __nv_bfloat16* relu_mask;  // optional (TMA-store path): C[m,n] = relu_mask[m*ldc+n] > 0 ? value : 0 (relu backward)
   float* colsum;               // optional (MN-major A only): colsum[m] += sum_k A(m, k) -- the bias gradient of a wgrad product
   unsigned long long* probe;   // debugging aid (fira_debug_set_probe): CTA (0,0,0) stamps %globaltimer at its phase boundaries
 };
@@ -253,8 +254,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = mrow0 + lane;
       const float rsm = (p.rs && m < p.M) ? p.rs[m] : 0.f;
       if (warp == 2 && lane == 0) stamp(p, 6);
+      const __nv_bfloat16* mrow = nullptr;          // relu-backward mask: this lane's row of the forward activations
+      if (p.relu_mask && m < p.M) {
+        mrow = p.relu_mask + (long)m * p.ldc + n0;
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g)
+          if (n0 + g * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + g * 64));
+      }
 #pragma unroll 1
       for (int g = 0; g < BN / 64; ++g) {
+        uint4 mk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mk[j] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // 1.0: keep
+        if (mrow != nullptr && n0 + g * 64 + 63 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mk[j] = *reinterpret_cast<const uint4*>(mrow + g * 64 + j * 8);
+        } else if (mrow != nullptr) {
+          __nv_bfloat16* me = reinterpret_cast<__nv_bfloat16*>(mk);
+          for (int j = 0; j < 64; ++j) if (n0 + g * 64 + j < p.N) me[j] = mrow[g * 64 + j];
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
@@ -285,6 +303,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 8; ++j) {
               v[j] = fmaf(rsm, kk[j], __uint_as_float(r[q * 8 + j]) + bb[j]);
               if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            }
+            {
+              const __nv_bfloat162* mp = reinterpret_cast<const __nv_bfloat162*>(&mk[h * 4 + q]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(mp[j]);
+                if (!(f.x > 0.f)) v[2 * j] = 0.f;
+                if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+              }
             }
             uint4 o;
             __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -499,7 +526,7 @@ extern "C" int fira_debug_set_probe(void* probe) {
 namespace {
 int gemm_tc_impl(const void* A, long lda, int a_kmajor, const void* B, long ldb, int b_kmajor, void* C, long ldc,
                  int c_is_bf16, int M, int N, int K, const float* bias, const float* rs, const float* rc, int relu,
-                 int accumulate, int splits, float* colsum, void* stream) {
+                 int accumulate, int splits, float* colsum, void* stream, const void* relu_mask = nullptr) {
   FIRA_CHECK_ARG(A && B && C, FIRA_ERR_ARG, "gemm_bf16_tc: null operand");
   FIRA_CHECK_ARG(M > 0 && N > 0 && K > 0, FIRA_ERR_SHAPE, "gemm_bf16_tc: M=%d N=%d K=%d", M, N, K);
   FIRA_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, FIRA_ERR_ALIGN, "gemm_bf16_tc: lda/ldb must be multiples of 8");
@@ -537,8 +564,10 @@ int gemm_tc_impl(const void* A, long lda, int a_kmajor, const void* B, long ldb,
     rc_ = make_map(&tc, C, M, N, ldc, 64, 32);
     if (rc_) return rc_;
   }
+  FIRA_CHECK_ARG(relu_mask == nullptr || tma_store, FIRA_ERR_ARG,
+                 "gemm_bf16_tc: the relu mask needs the TMA-store epilogue (bf16 C, no accumulate, no split-K)");
   TcParams p{C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits, per, a_kmajor, b_kmajor, rotate_on() ? 1 : 0,
-             tma_store, colsum,
+             tma_store, (const __nv_bfloat16*)relu_mask, colsum,
              g_probe.load(std::memory_order_relaxed)};
   if (splits > 1 && !accumulate) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
@@ -558,6 +587,16 @@ extern "C" int fira_gemm_bf16_tc(const void* A, long lda, int a_kmajor, const vo
                                  const float* rc, int relu, int accumulate, int splits, void* stream) {
   return gemm_tc_impl(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, c_is_bf16, M, N, K, bias, rs, rc, relu, accumulate, splits,
                       nullptr, stream);
+}
+
+// Input-gradient product through a relu: dx[m,n] = h[m,n] > 0 ? sum_k dy[m,k] W[k,n] : 0 -- dy K-major, W read MN-major
+// (the nn.Linear weight [out = k, in = n] as it lies in memory), h = the forward activations (same shape / leading
+// dimension as dx).  The relu backward of the FeedForward block folded into the epilogue of its input-gradient product.
+extern "C" int fira_gemm_bf16_tc_dx_relu(const void* dy, long lddy, const void* W, long ldw, void* dx, long lddx,
+                                         const void* h, int M, int N, int K, void* stream) {
+  FIRA_CHECK_ARG(h != nullptr && fira_aligned16(h), FIRA_ERR_ARG, "gemm_bf16_tc_dx_relu: mask");
+  FIRA_CHECK_ARG(tma_store_on(), FIRA_ERR_ARG, "gemm_bf16_tc_dx_relu: needs the TMA-store epilogue (FIRA_GEMM_TMA_STORE=0 is set)");
+  return gemm_tc_impl(dy, lddy, 1, W, ldw, 0, dx, lddx, 1, M, N, K, nullptr, nullptr, nullptr, 0, 0, 1, nullptr, stream, h);
 }
 
 // Weight-gradient product with the bias gradient folded in: C[M,N] = A^T-stored (MN-major) A times B as above, and

@@ -123,11 +123,17 @@ def gemm_tc(A, lda, a_kmajor, Bm, ldb, b_kmajor, C, ldc, M, N, K, bias=None, rs=
     return C
 
 
+# CTAs a split-K weight-gradient product may spread over.  These products run on the side streams NEXT TO the main
+# chain: filling all 148 SMs shortens the product itself but takes the SMs (and, through the fp32 atomics of split-K,
+# the L2 atomic throughput) away from the critical path.
+WGRAD_CTAS = max(1, int(os.environ.get("FIRA_WGRAD_CTAS", "148")))
+
+
 def _tc_splits(tiles, kblocks):
-    """split-K factor that brings a small-output GEMM to ~2 CTAs per SM"""
-    if tiles >= 148:
+    """split-K factor of a small-output GEMM: at least 8 k-blocks per split, at most WGRAD_CTAS CTAs in all"""
+    if tiles >= WGRAD_CTAS:
         return 1
-    return max(1, min(kblocks // 8 if kblocks >= 16 else 1, _ceil(148, tiles)))
+    return max(1, min(kblocks // 8 if kblocks >= 16 else 1, _ceil(WGRAD_CTAS, tiles)))
 
 
 def colsum(x, ld, M, N, weight=None, x_off=0, dtype=None, out=None):
@@ -186,6 +192,18 @@ class Prec:
             out = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
         return gemm_tc(dy, ld_dy, 1, self.w(W), K, 0, out, K, M, K, N, accumulate=accumulate, a_off=dy_off)
 
+    def linear_dx_relu(self, dy, ld_dy, W, M, h):
+        """dx = relu'(h) * (dy W): the relu backward of the FeedForward block (gnn_transformer.py:172); bf16 mode: folded
+        into the epilogue of the input-gradient product (fira_gemm_bf16_tc_dx_relu) unless FIRA_DX_RELU=0"""
+        N, K = W.shape
+        if self.bf16 and FUSE_DX_RELU:
+            out = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
+            call("fira_gemm_bf16_tc_dx_relu", _ptr(dy), ld_dy, _ptr(self.w(W)), K, _ptr(out), K, _ptr(h), M, K, N, _stream())
+            return out
+        out = self.linear_dx(dy, ld_dy, W, M)
+        call("fira_relu_bwd", _ptr(h), _ptr(out), M * K, self.code, _stream())
+        return out
+
     # dW = dy^T x   (fp32 result in both modes)
     def linear_dw(self, dy, ld_dy, x, ldx, M, N, K, dy_off=0, x_off=0, out=None, dbias=None):
         """dW = dy^T x.  dbias: zero-filled fp32 [N] that receives the bias gradient colsum(dy) -- in bf16 mode from the
@@ -204,6 +222,20 @@ class Prec:
         if dbias is not None:
             colsum(dy, ld_dy, M, N, x_off=dy_off, out=dbias)
         return gemm_tc(dy, ld_dy, 0, x, ldx, 0, dW, K, N, K, M, splits=splits, a_off=dy_off, b_off=x_off)
+
+    def linear_ln(self, x, W, b, resid, gamma, beta, outA, outB, split, rows, p, seed, sid, rs=None, rc=None):
+        """z = x W^T + b (+ rs rc^T);  out = LN(dropout(z) + resid) -> (z, stats).  bf16 mode: ONE launch
+        (fira_gemm_ln_fwd, csrc/gemm_ln.cu) unless FIRA_GEMM_LN=0; fp32 mode: the GEMM, then the LayerNorm kernel."""
+        N, K = W.shape
+        if self.bf16 and N == D and FUSE_GEMM_LN:
+            z = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+            stats = torch.empty((2, rows), dtype=torch.float32, device=x.device)
+            call("fira_gemm_ln_fwd", _ptr(x), K, _ptr(self.w(W)), _ptr(b), _ptr(rs), _ptr(rc), _ptr(resid), _ptr(gamma),
+                 _ptr(beta), _ptr(z), _ptr(outA), _ptr(outB) if outB is not outA else None, split, _ptr(stats),
+                 _ptr(stats, rows), rows, K, float(p), seed, _ptr(self.seed_ctr), sid, _stream())
+            return z, stats
+        z = self.linear(x, W, b, rs=rs, rc=rc, M=rows)
+        return z, self.ln_fwd(z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid)
 
     def ln_fwd(self, z, resid, gamma, beta, outA, outB, split, rows, p, seed, sid):
         stats = torch.empty((2, rows), dtype=torch.float32, device=z.device)
@@ -246,6 +278,11 @@ N_SIDE = max(1, int(os.environ.get("FIRA_SIDE_STREAMS", "8")))
 # the 256^3 fp32 products of the GCN weight merge (W2 W1 and its two adjoints) are 16 CTAs of the 64 x 64 tile: split-K
 # spreads them over 64 CTAs (15.9 us per product in the step timeline); bf16 mode only -- the fp32 parity mode keeps the
 # deterministic single-pass sum
+# fira_gemm_ln_fwd (Linear + dropout + residual + LayerNorm in one launch) is OPT-IN: a 128-row tile owns whole rows, so a
+# decoder product runs on 15 CTAs that each pull 256 KB and make two passes over the accumulator -- measured 0.09 ms per
+# step SLOWER than the 60-CTA product followed by the LayerNorm kernel (profiles/bench_r2_ab_run_l.jsonl)
+FUSE_GEMM_LN = os.environ.get("FIRA_GEMM_LN", "0") != "0"
+FUSE_DX_RELU = os.environ.get("FIRA_DX_RELU", "1") != "0" and os.environ.get("FIRA_GEMM_TMA_STORE", "1") != "0"
 MERGE_SPLITS = max(1, int(os.environ.get("FIRA_MERGE_SPLITS", "4")))
 _TURN = [0]            # rotation shared by every Fork, so consecutive Forks do not all start on the same stream
 
@@ -265,6 +302,8 @@ class Fork:
         key = (device.index if device.index is not None else torch.cuda.current_device())
         if key not in _SIDE_STREAMS:
             _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(N_SIDE)]
+            if os.environ.get("FIRA_EXPERIMENT_SKIP_SIDE", "0") != "0":     # timing experiment only, see _lib.call
+                _lib.SKIP_STREAMS = {st.cuda_stream for st in _SIDE_STREAMS[key]}
         self.sides = _SIDE_STREAMS[key][:n_side] if n_side else _SIDE_STREAMS[key]
         self.side = self.sides[0]
         self.keep = []
@@ -298,20 +337,35 @@ class Prefetch:
         self.event = None
 
 
-def _prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2, fused=True):
+def _prep_encoder_layer(pr, fork, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2, fused=True):
+    """Weight-only preparation of one encoder layer, as THREE independent groups on different side streams (each a few
+    tiny launches): the 4-row value table, the merged GCN weight W2 W1 (+ its bf16 operand copies), the merged bias
+    W2 b1.  Returns the tensors and one event per group; the consumer waits for a group right before it needs it."""
     f32 = dict(dtype=torch.float32, device=Wq.device)
-    Wqk = _optim.cat_rows((Wq, Wk))                                  # views when optim.FlatAdam laid them out back to back
-    bqk = _optim.cat_rows((bq, bk))
-    Vtab = linear(mark_emb, Wv, bv)                                # fp32 [4, 256]: value has 4 distinct rows
-    Wc = torch.empty((D, D), **f32)                                # W2 @ W1
-    gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=MERGE_SPLITS if pr.bf16 else 1)
-    c1 = torch.empty((D,), **f32)                                  # W2 @ b1
-    gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
-    for w in (Wqk, Wo, Wc):
-        pr.w(w)                                                    # bf16 operand copies (no-op in fp32 mode)
-    # the fused GCN backward multiplies by Wc itself ([out, in] read as K = out): its B operand is Wc^T stored K-major
-    WcT16 = Wc.t().contiguous().to(torch.bfloat16) if (pr.bf16 and fused) else None
-    return Wqk, bqk, Vtab, Wc, c1, WcT16
+
+    def done():
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+    with fork(mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo):
+        Wqk = _optim.cat_rows((Wq, Wk))                              # views when optim.FlatAdam laid them out back to back
+        bqk = _optim.cat_rows((bq, bk))
+        Vtab = linear(mark_emb, Wv, bv)                            # fp32 [4, 256]: value has 4 distinct rows
+        for w in (Wqk, Wo):
+            pr.w(w)                                                # bf16 operand copies (views of the mirror / no-op in fp32)
+        ev_comb = done()
+    with fork(W1, W2):
+        Wc = torch.empty((D, D), **f32)                            # W2 @ W1
+        gemm_raw(_ptr(W2), D, 1, _ptr(W1), D, 0, _ptr(Wc), D, D, D, D, splits=MERGE_SPLITS if pr.bf16 else 1)
+        pr.w(Wc)
+        # the fused GCN backward multiplies by Wc itself ([out, in] read as K = out): its B operand is Wc^T stored K-major
+        WcT16 = Wc.t().contiguous().to(torch.bfloat16) if (pr.bf16 and fused) else None
+        ev_wc = done()
+    with fork(W2, b1):
+        c1 = torch.empty((D,), **f32)                              # W2 @ b1
+        gemm_raw(_ptr(W2), D, 1, _ptr(b1), D, 1, _ptr(c1), 1, D, 1, D, splits=1)
+        ev_c1 = done()
+    return (Wqk, bqk, Vtab, Wc, c1, WcT16), (ev_comb, ev_wc, ev_c1)
 
 
 def prefetch_decoder(bf16, lp, device):
@@ -411,27 +465,27 @@ class EncoderFn(torch.autograd.Function):
         fork = Fork(dev)
         preps, events = [], []
         for i in range(L):
-            with fork(mark_emb, *lp[i * 16:(i + 1) * 16]):
-                Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
-                preps.append(_prep_encoder_layer(pr, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2, fused=fused))
-                ev = torch.cuda.Event()
-                ev.record()
-                events.append(ev)
+            Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
+            t, e = _prep_encoder_layer(pr, fork, mark_emb, Wq, bq, Wk, bk, Wv, bv, Wo, W1, b1, W2, fused=fused)
+            preps.append(t)
+            events.append(e)
         for i in range(L):
             Wq, bq, Wk, bk, Wv, bv, Wo, bo, clw, clb, W1, b1, W2, b2, glw, glb = lp[i * 16:(i + 1) * 16]
             sid = cfg["stream_base"] + i * 8
-            torch.cuda.current_stream().wait_event(events[i])
+            cur = torch.cuda.current_stream()
+            cur.wait_event(events[i][0])                               # q|k views, value table
             Wqk, bqk, Vtab, Wc, c1, WcT16 = preps[i]
             # ---- Combination (gnn_transformer.py:192-205, combination_layer.py:7-17)
             QK = pr.linear(Xc, Wqk, bqk)                               # [Mc, 512] = [q | k]
             Cd = pr.empty((Mc, D), dev)
             call("fira_comb_gate_fwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(Cd), Mc, D, D // heads,
                  float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
-            Zc = pr.linear(Cd, Wo, bo)
-            st_c = pr.ln_fwd(Zc, Xc, clw, clb, Gin, Gin, Mc, Mc, p_comb, seed, sid + 1)   # -> Gin[:Mc]
+            Zc, st_c = pr.linear_ln(Cd, Wo, bo, Xc, clw, clb, Gin, Gin, Mc, Mc, p_comb, seed, sid + 1)   # -> Gin[:Mc]
             # ---- GCN (gnn_transformer.py:74-86)
             Xc_n = pr.empty((Mc, D), dev)
             Gin_n = pr.empty((R, D), dev)
+            cur.wait_event(events[i][1])                               # merged weight W2 W1
+            cur.wait_event(events[i][2])                               # merged bias W2 b1
             if fused:
                 G = None
                 Z = pr.empty((R, D), dev)
@@ -443,8 +497,7 @@ class EncoderFn(torch.autograd.Function):
                 G = pr.empty((R, D), dev)
                 call("fira_gcn_aggregate", _ptr(edges.rowptr), _ptr(edges.col), _ptr(edges.val), _ptr(Gin), None,
                      _ptr(G), B, n_code, n_sub, n_ast, D, pr.code, st)
-                Z = pr.linear(G, Wc, b2, rs=rs, rc=c1)
-                st_g = pr.ln_fwd(Z, Gin, glw, glb, Xc_n, Gin_n, Mc, R, p_gcn, seed, sid + 2)
+                Z, st_g = pr.linear_ln(G, Wc, b2, Gin, glw, glb, Xc_n, Gin_n, Mc, R, p_gcn, seed, sid + 2, rs=rs, rc=c1)
             saved.append((Xc, QK, Vtab, Cd, Zc, st_c, Gin, G, Z, st_g, Wqk, Wc, c1, WcT16))
             Xc, Gin = Xc_n, Gin_n
         memory = pr.empty((B, n_code + n_sub, D), dev)
@@ -500,13 +553,21 @@ class EncoderFn(torch.autograd.Function):
                 else:
                     d_c1 = colsum(dZ, D, R, D, weight=rs)
                     dWc = pr.linear_dw(dZ, D, G, D, R, D, D, dbias=d_b2)
+                ev_dwc = torch.cuda.Event()
+                ev_dwc.record()
+                fork.keep.extend((dWc, d_c1))
+            # the three fp32 adjoints of the weight merge are independent of each other: two more side streams (the
+            # last layer's chain dWc -> d_W2 -> d_W1 -> d_b1 used to end 60 us after the main stream)
+            with fork():
+                torch.cuda.current_stream().wait_event(ev_dwc)
                 d_W2 = _gdest(W2, (D, D))               # dWc W1^T + d_c1 b1^T
                 gemm_raw(_ptr(dWc), D, 1, _ptr(W1), D, 1, _ptr(d_W2), D, D, D, D, rs=d_c1, rc=b1, splits=MERGE_SPLITS if pr.bf16 else 1)
+            with fork():
+                torch.cuda.current_stream().wait_event(ev_dwc)
                 d_W1 = _gdest(W1, (D, D))               # W2^T dWc
                 gemm_raw(_ptr(W2), D, 0, _ptr(dWc), D, 0, _ptr(d_W1), D, D, D, D, splits=MERGE_SPLITS if pr.bf16 else 1)
                 d_b1 = _gdest(b1, (D,))                 # W2^T d_c1
                 gemm_raw(_ptr(W2), D, 0, _ptr(d_c1), 1, 0, _ptr(d_b1), 1, D, 1, D, splits=1)
-                fork.keep.extend((dWc, d_c1))
             if not fused:
                 dG = pr.linear_dx(dZ, D, Wc, R)
                 call("fira_gcn_aggregate", _ptr(et.rowptr), _ptr(et.col), _ptr(et.val), _ptr(dG), _ptr(dRes),
@@ -523,11 +584,13 @@ class EncoderFn(torch.autograd.Function):
             dVtab = torch.zeros((4, D), **f32)
             call("fira_comb_gate_bwd", _ptr(QK), 2 * D, _ptr(Vtab), _ptr(mark), _ptr(dCd), _ptr(dQK), _ptr(dVtab),
                  Mc, D, D // heads, float(p_comb), seed, _ptr(pr.seed_ctr), sid + 0, pr.code, st)
-            with fork(dQK, Xc, dVtab, mark_emb, Wv, d_mark_emb, lane=0):     # d_mark_emb accumulates across layers
+            with fork(dQK, Xc):
                 d_bqk = _gdest((bq, bk), (2 * D,), zero=True)
                 d_Wqk = pr.linear_dw(dQK, 2 * D, Xc, D, Mc, 2 * D, D, out=_gdest((Wq, Wk), (2 * D, D)), dbias=d_bqk)
+            with fork(dVtab, mark_emb, Wv):
                 d_Wv = linear_dw(dVtab, D, mark_emb, D, 4, D, D, out=_gdest(Wv, (D, D)))
                 d_bv = colsum(dVtab, D, 4, D, out=_gdest(bv, (D,), zero=True))
+            with fork(dVtab, Wv, lane=0):                           # d_mark_emb accumulates across layers: one stream, in order
                 linear_dx(dVtab, D, Wv, 4, out=d_mark_emb, accumulate=True)
             pr.linear_dx(dQK, 2 * D, Wqk, Mc, out=dXc_n, accumulate=True)
             grads[i * 16:(i + 1) * 16] = [d_Wqk[:D], d_bqk[:D], d_Wqk[D:], d_bqk[D:], d_Wv, d_bv, d_Wo, d_bo,
@@ -593,9 +656,8 @@ class DecoderFn(torch.autograd.Function):
             st1 = torch.empty((B, H, T, 2), **f32)
             call("fira_attn_fwd", _ptr(QKV), 3 * D, _ptr(QKV, D), 3 * D, _ptr(QKV, 2 * D), 3 * D, _ptr(tar_mask), 1,
                  _ptr(ctx1), D, _ptr(st1), B, H, T, T, D // H, pr.code, st)
-            Z1 = pr.linear(ctx1, sWo, sbo)
             X1 = pr.empty((Mt, D), dev)
-            ls1 = pr.ln_fwd(Z1, X, slw, slb, X1, X1, Mt, Mt, p, seed, sid + 0)
+            Z1, ls1 = pr.linear_ln(ctx1, sWo, sbo, X, slw, slb, X1, X1, Mt, Mt, p, seed, sid + 0)
             # ---- cross-attention over the encoder memory (gnn_transformer.py:120)
             Q = pr.linear(X1, cWq, cbq)
             ctx2 = pr.empty((Mt, D), dev)
@@ -606,14 +668,12 @@ class DecoderFn(torch.autograd.Function):
             else:
                 call("fira_attn_fwd", _ptr(Q), D, _ptr(KV, i * 2 * D), ldkv, _ptr(KV, i * 2 * D + D), ldkv,
                      _ptr(mem_mask), 0, _ptr(ctx2), D, _ptr(st2), B, H, T, S, D // H, pr.code, st)
-            Z2 = pr.linear(ctx2, cWo, cbo)
             X2 = pr.empty((Mt, D), dev)
-            ls2 = pr.ln_fwd(Z2, X1, clw, clb, X2, X2, Mt, Mt, p, seed, sid + 1)
+            Z2, ls2 = pr.linear_ln(ctx2, cWo, cbo, X1, clw, clb, X2, X2, Mt, Mt, p, seed, sid + 1)
             # ---- feed-forward (gnn_transformer.py:170-174)
             Hh = pr.linear(X2, fW1, fb1, relu=True)                       # [Mt, 1024]
-            Z3 = pr.linear(Hh, fW2, fb2)
             X3 = pr.empty((Mt, D), dev)
-            ls3 = pr.ln_fwd(Z3, X2, flw, flb, X3, X3, Mt, Mt, p, seed, sid + 2)
+            Z3, ls3 = pr.linear_ln(Hh, fW2, fb2, X2, flw, flb, X3, X3, Mt, Mt, p, seed, sid + 2)
             saved.append((X, Wqkv, QKV, ctx1, st1, Z1, ls1, X1, Q, ctx2, st2, Z2, ls2, X2, Hh, Z3, ls3))
             X = X3
         ctx.saved = saved
@@ -652,8 +712,7 @@ class DecoderFn(torch.autograd.Function):
             with fork(dZ3, Hh):
                 d_fb2 = _gdest(fb2, (D,), zero=True)
                 d_fW2 = pr.linear_dw(dZ3, D, Hh, F, Mt, D, F, out=_gdest(fW2, (D, F)), dbias=d_fb2)
-            dHh = pr.linear_dx(dZ3, D, fW2, Mt)                           # [Mt, 1024]
-            call("fira_relu_bwd", _ptr(Hh), _ptr(dHh), Mt * F, pr.code, st)
+            dHh = pr.linear_dx_relu(dZ3, D, fW2, Mt, Hh)                  # [Mt, 1024], relu backward in the epilogue
             with fork(dHh, X2):
                 d_fb1 = _gdest(fb1, (F,), zero=True)
                 d_fW1 = pr.linear_dw(dHh, F, X2, D, Mt, F, D, out=_gdest(fW1, (F, D)), dbias=d_fb1)
@@ -810,10 +869,12 @@ class HeadFn(torch.autograd.Function):
             call("fira_copy_scores_bwd", _ptr(src), _ptr(tgt), _ptr(Wres), _ptr(dsc), _ptr(active), _ptr(d_src),
                  _ptr(d_tgt), _ptr(d_wres), _ptr(d_bres), B, T, S, D, pr.code, st)
         fork = Fork(dev)
-        with fork(d_src, memory2, dlogits, dec2, dgl, dec32, d_tgt):
+        with fork(d_src, memory2):                           # three independent groups, three side streams
             d_Ws = pr.linear_dw(d_src, D, memory2, D, Ms, D, D, out=_gdest(Ws, (D, D)))
+        with fork(dlogits, dec2):
             d_bout = _gdest(bout, (V,), zero=True)
             d_Wout = pr.linear_dw(dlogits, ldl, dec2, D, Mt, V, D, out=_gdest(Wout, (V, D)), dbias=d_bout)
+        with fork(dgl, dec32, d_tgt):
             d_bp = colsum(dgl, 2, Mt, 2, out=_gdest(bp, (2,), zero=True))
             d_Wp = linear_dw(dgl, 2, dec32, D, Mt, 2, D, out=_gdest(Wp, (2, D)))
             d_Wt = linear_dw(d_tgt, D, dec32, D, Mt, D, D, out=_gdest(Wt, (D, D)))

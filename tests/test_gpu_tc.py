@@ -91,3 +91,63 @@ def test_weight_grad_with_folded_bias_grad(rows, N, K, ld):
         pr.linear_dw(dy, ld, x, K, rows, N, K, out=dW, dbias=db)
         close(dW, ref_w)
         close(db, ref_b)
+
+
+@pytest.mark.parametrize("rows,K,split,rank1,p", [(1920, 256, None, False, 0.0), (1920, 1024, None, False, 0.1), (300, 256, None, False, 0.0),
+                                                  (11000, 256, 3500, True, 0.2), (333, 256, 100, True, 0.0), (128, 256, 0, False, 0.0)])
+def test_gemm_ln_fused_equals_gemm_then_layernorm(rows, K, split, rank1, p):
+    """fira_gemm_ln_fwd (one launch) against fira_gemm_bf16_tc + fira_ln_residual_fwd (the sequence it replaces): same z,
+    same dropout masks, same statistics, same normalised rows in both outputs"""
+    from fira_icse_b200 import ops as o
+    D = 256
+    x, W = rnd(rows, K, seed=1), rnd(D, K, seed=2) * 0.1
+    resid = rnd(rows, D, seed=3)
+    g = torch.Generator().manual_seed(4)
+    b, gamma, beta = (torch.randn(D, generator=g).to(DEV) for _ in range(3))
+    rs = torch.randn(rows, generator=g).to(DEV) if rank1 else None
+    rc = torch.randn(D, generator=g).to(DEV) if rank1 else None
+    pr = o.Prec(True)
+    sp = rows if split is None else split
+    seed, sid = 1234, 7
+
+    def run(fused):
+        o.FUSE_GEMM_LN = fused
+        outA = torch.full((max(sp, 1), D), 5.0, device=DEV, dtype=torch.bfloat16)
+        outB = torch.full((rows, D), 5.0, device=DEV, dtype=torch.bfloat16) if split is not None else outA
+        z, st = pr.linear_ln(x, W.to(torch.bfloat16), b, resid, gamma, beta, outA, outB, sp, rows, p, seed, sid, rs=rs, rc=rc)
+        torch.cuda.synchronize()
+        return z.float(), st.clone(), outA.float(), outB.float()
+    try:
+        z1, s1, a1, b1 = run(True)
+        z0, s0, a0, b0 = run(False)
+    finally:
+        o.FUSE_GEMM_LN = True
+    close(z1, z0, rtol=1e-2)
+    torch.testing.assert_close(s1, s0, rtol=2e-2, atol=2e-2)
+    if sp > 0:
+        close(a1[:sp], a0[:sp], rtol=2e-2)
+    if split is not None:
+        close(b1[sp:], b0[sp:], rtol=2e-2)
+        assert (b1[:sp // 32 * 32] == 5.0).all()       # rows below the split's 32-row slab are not written to outB
+    if split is not None and sp > 0:
+        assert a1.shape[0] == sp
+
+
+@pytest.mark.parametrize("rows,N,K", [(1920, 256, 1024), (300, 72, 200), (128, 64, 64)])
+def test_input_grad_through_relu(rows, N, K):
+    """fira_gemm_bf16_tc_dx_relu: dx = relu'(h) * (dy W) in one launch == the product followed by fira_relu_bwd"""
+    from fira_icse_b200 import ops as o
+    dy, W = rnd(rows, N, seed=1), rnd(N, K, seed=2)
+    h = torch.relu(rnd(rows, K, seed=3))
+    pr = o.Prec(True)
+    try:
+        o.FUSE_DX_RELU = True
+        a = pr.linear_dx_relu(dy, N, W, rows, h).float()
+        o.FUSE_DX_RELU = False
+        b = pr.linear_dx_relu(dy, N, W, rows, h).float()
+    finally:
+        o.FUSE_DX_RELU = True
+    ref = (dy.float() @ W.float()) * (h > 0)
+    close(a, ref, rtol=1e-2)
+    close(b, ref, rtol=1e-2)
+    assert ((a == 0) == (b == 0)).all()

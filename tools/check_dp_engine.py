@@ -28,6 +28,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--layout", default="packed", choices=["packed", "padded"])
     ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "flat_adam"],
+                    help="flat_adam: optim.FlatAdam on both sides (gradients written into the flat buffers, all-reduced in "
+                         "place, Adam of the head/decoder parameters behind the encoder backward); losses compared at 2e-3 "
+                         "(Adam amplifies summation-order noise), parameters by the size of one Adam step")
     a = ap.parse_args()
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -61,8 +65,15 @@ def main():
         d[5] = PackedEdges.from_host(*h[5], B, 650, dev)
         return d
     lr = 2e-3
-    dp = DataParallelStep(m_ref, lambda ps: torch.optim.SGD(ps, lr=lr))
-    eng = GraphedTrainStep(m_eng, B, lambda ps: torch.optim.SGD(ps, lr=lr), edge_capacity=65536)
+    if a.optimizer == "flat_adam":
+        from fira_icse_b200.optim import FlatAdam
+        lr = 1e-4
+        dp = DataParallelStep(m_ref, lambda ps: FlatAdam(ps, lr=lr, groups=m_ref.flat_groups()))
+        eng = GraphedTrainStep(m_eng, B, lambda ps: FlatAdam(ps, lr=lr, groups=m_eng.flat_groups()), edge_capacity=65536)
+    else:
+        dp = DataParallelStep(m_ref, lambda ps: torch.optim.SGD(ps, lr=lr))
+        eng = GraphedTrainStep(m_eng, B, lambda ps: torch.optim.SGD(ps, lr=lr), edge_capacity=65536)
+    loss_tol, param_tol = (2e-3, 6 * lr * a.steps) if a.optimizer == "flat_adam" else (2e-4, 5e-4)
     assert eng.split, "the N > 1 engine should run the split (overlapped) step"
     worst = 0.0
     ok = True
@@ -72,6 +83,7 @@ def main():
             # eager reference of the packed layout: forward_packed + global token count + one flat all-reduce
             pb = h.to(dev)
             dp.bucket.zero()
+            dp.optimizer.zero_grad(set_to_none=True)
             ls, nt = m_ref.forward_packed(pb, "train")
             ng = nt.to(torch.float32).reshape(1).clone()
             lg = ls.detach().reshape(1).clone()
@@ -90,7 +102,7 @@ def main():
         loss_eng = (tot[0] / tot[1]).item()
         rel = abs(loss_eng - loss_ref) / abs(loss_ref)
         worst = max(worst, rel)
-        ok &= rel <= 2e-4
+        ok &= rel <= loss_tol
     pmax = 0.0
     for (k, p), (_, q) in zip(m_ref.named_parameters(), m_eng.named_parameters()):
         pmax = max(pmax, (p - q).abs().max().item())
@@ -101,10 +113,10 @@ def main():
     drift = (flat - other).abs().max().item()
     res = torch.tensor([worst, pmax, drift], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
-    ok = ok and res[1].item() <= 5e-4 and res[2].item() == 0.0
+    ok = ok and res[1].item() <= param_tol and res[2].item() == 0.0
     if rank == 0:
         print(json.dumps({"check": "GraphedTrainStep(split, NCCL) vs eager DataParallelStep", "layout": a.layout,
-                          "world": world, "steps": a.steps, "worst_loss_rel_diff": res[0].item(),
+                          "optimizer": a.optimizer, "world": world, "steps": a.steps, "worst_loss_rel_diff": res[0].item(),
                           "max_param_abs_diff": res[1].item(), "replica_drift": res[2].item(), "ok": bool(ok)}), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
