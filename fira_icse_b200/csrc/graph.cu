@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(const int* __restrict__ r
 // A lane's features are INTERLEAVED in 8-feature chunks (chunk j of lane l = features j*LPR*8 + l*8 .. +7), so
 // one load/store instruction of a row group covers a contiguous LPR*16 B (bf16) span; with the blocked layout
 // (lane l = features l*F ..) every instruction touched half of each 32-B sector (ncu: 49 % excessive sectors).
-template <typename T, int LPR>     // LPR lanes per destination row (16 or 8): 32/LPR rows in flight per warp
+template <typename T, int LPR, int UNROLL = 1>     // LPR lanes per destination row (16 or 8): 32/LPR rows in flight per warp
 __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                             const float* __restrict__ val, const T* __restrict__ x,
                                                             const T* __restrict__ addend, T* __restrict__ y, Segs s,
@@ -218,7 +218,25 @@ __global__ void __launch_bounds__(256) csr_spmm_part_kernel(const int* __restric
       const int n = min(LPR, e1 - eb);
       int c = 0; float w = 0.f;
       if (hl < n) { c = col[eb + hl]; w = val[eb + hl]; }
-      for (int t = 0; t < n; ++t) {
+      int t = 0;
+      if constexpr (UNROLL == 2) {       // variant 7 (A/B): two neighbour rows in flight per lane group, CSR order kept
+        for (; t + 1 < n; t += 2) {
+          const int c0 = __shfl_sync(hmask, c, hbase + t), c1 = __shfl_sync(hmask, c, hbase + t + 1);
+          const float w0 = __shfl_sync(hmask, w, hbase + t), w1 = __shfl_sync(hmask, w, hbase + t + 1);
+          float v0[F], v1[F];
+          const T* p0 = x + seg_row(s, b, c0) * D + hl * 8;
+          const T* p1 = x + seg_row(s, b, c1) * D + hl * 8;
+#pragma unroll
+          for (int q = 0; q < F; q += 8) Act<T>::load8(p0 + q * LPR, v0 + q);
+#pragma unroll
+          for (int q = 0; q < F; q += 8) Act<T>::load8(p1 + q * LPR, v1 + q);
+#pragma unroll
+          for (int k = 0; k < F; ++k) acc[k] = fmaf(w0, v0[k], acc[k]);
+#pragma unroll
+          for (int k = 0; k < F; ++k) acc[k] = fmaf(w1, v1[k], acc[k]);
+        }
+      }
+      for (; t < n; ++t) {
         const int c0 = __shfl_sync(hmask, c, hbase + t);
         const float w0 = __shfl_sync(hmask, w, hbase + t);
         float v0[F];
@@ -499,10 +517,13 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
   Segs s{B, n_code, n_sub, n_ast};
   const int N = n_code + n_sub + n_ast;
   const long R = (long)B * N;
-  // measured defaults (profiles/spmm_variants_r1.md): fp32 rows (1 KB) -> one warp per row; bf16 rows (512 B) ->
-  // half a warp per row (two rows in flight per warp: 23 -> 19 us at B = 64).  FIRA_SPMM_VARIANT overrides (A/B runs).
+  // measured default (profiles/scatter_variants_r2.jsonl, graph-replayed launches, 64 / 512 commits): a QUARTER warp per
+  // destination row (variant 8: four independent rowptr -> (col,val) -> neighbour-row chains per warp, 32 features =
+  // 64-128 B per lane and neighbour row) -- 0.52 / 0.65 of the measured HBM peak in bf16 and 0.70 in fp32, against 0.46 /
+  // 0.58 / 0.62 for half a warp per row (variant 4) and 0.38 / 0.44 / 0.59 for a whole warp (variant 1).
+  // FIRA_SPMM_VARIANT overrides (A/B runs).
   static const int forced = [] { const char* e = getenv("FIRA_SPMM_VARIANT"); return e ? atoi(e) : 0; }();
-  const int variant = forced ? forced : (dtype == FIRA_BF16 ? 4 : 1);
+  const int variant = forced ? forced : 8;
   if (variant == 1) {                      // round-1 baseline kernel, kept for A/B profiling
     long ctas = (R + 7) / 8;
     const long cap = 148L * 8 * 4;
@@ -515,6 +536,26 @@ int fira_gcn_aggregate(const int* rowptr, const int* col, const float* val, cons
     int grid = (int)(ctas < cap ? ctas : cap);
     DISPATCH_T(dtype, launch_k(csr_spmm_part_kernel<T, 16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+  } else if (variant >= 7 && variant <= 10) {
+    // 7: half a warp per row, two neighbour rows in flight; 8 (default): a quarter warp per row; 9: an eighth of a warp per
+    // row (bf16); 10: a quarter warp per row, two neighbour rows in flight
+    const int rows_per_cta = variant == 7 ? 16 : (variant == 9 ? 64 : 32);
+    long ctas = (R + rows_per_cta - 1) / rows_per_cta;
+    const long cap = 148L * 8 * 4;
+    int grid = (int)(ctas < cap ? ctas : cap);
+    if (variant == 7) {
+      DISPATCH_T(dtype, launch_k(csr_spmm_part_kernel<T, 16, 2>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    } else if (variant == 8) {
+      DISPATCH_T(dtype, launch_k(csr_spmm_part_kernel<T, 8, 1>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    } else if (variant == 9) {
+      DISPATCH_T(dtype, launch_k(csr_spmm_part_kernel<T, 4, 1>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    } else {
+      DISPATCH_T(dtype, launch_k(csr_spmm_part_kernel<T, 8, 2>, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+          rowptr, col, val, (const T*)x, (const T*)addend, (T*)y, s, N);)
+    }
   } else if (variant == 6) {                 // persistent one-wave grid, metadata pipelined two rows ahead (unmeasured)
     const int rows_per_cta = dtype == FIRA_BF16 ? 16 : 8;
     long ctas = (R + rows_per_cta - 1) / rows_per_cta;

@@ -354,7 +354,7 @@ class GraphedTrainStep:
         self._forward_backward(c)
         if self.world > 1:
             if self.flat_optims:
-                for o in self.opt_pair:
+                for o in self.flat_optims:
                     o.gather_grads()
                     dist.all_reduce(o.g, group=self.group)
                     for p, gv in zip(o.params, o.gviews):
