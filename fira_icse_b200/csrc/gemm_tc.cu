@@ -363,21 +363,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (p.splits > 1) {
         // split-K partials: lane <-> consecutive columns, so every RED.ADD of a warp covers one 128-B line
+        // 16-byte vector reductions (red.global.add.v4.f32, sm_90+): a lane owns 4 consecutive columns, so a row of the
+        // 128-column pass is ONE warp instruction instead of four -- the split-K weight-gradient products issue ~1 M
+        // fp32 reductions per launch
+        const bool vec = (p.ldc & 3) == 0;
         for (int rr = 0; rr < 32; ++rr) {
           const int m = mrow0 + rr;
           if (m >= p.M) break;
           const float rsm = (p.rs && first) ? p.rs[m] : 0.f;
           float* crow = (float*)p.C + (long)m * p.ldc;
 #pragma unroll
-          for (int jg = 0; jg < HB / 32; ++jg) {
-            const int n = n0 + hb + jg * 32 + lane;
-            if (n < p.N) {
-              float x = stg[(size_t)rr * PITCH + jg * 32 + lane];
+          for (int jg = 0; jg < HB / 128 + (HB % 128 ? 1 : 0); ++jg) {
+            const int c = jg * 128 + lane * 4;
+            const int n = n0 + hb + c;
+            if (c + 3 < HB && n < p.N) {
+              float4 x = *reinterpret_cast<const float4*>(stg + (size_t)rr * PITCH + c);
+              float* xv = reinterpret_cast<float*>(&x);
               if (first) {
-                if (p.bias) x += p.bias[n];
-                if (p.rs) x = fmaf(rsm, p.rc[n], x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < p.N) {
+                    if (p.bias) xv[j] += p.bias[n + j];
+                    if (p.rs) xv[j] = fmaf(rsm, p.rc[n + j], xv[j]);
+                  }
               }
-              atomicAdd(crow + n, x);
+              if (vec && n + 3 < p.N) {
+                atomicAdd(reinterpret_cast<float4*>(crow + n), x);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < p.N) atomicAdd(crow + n + j, xv[j]);
+              }
             }
           }
         }

@@ -152,3 +152,16 @@ def test_shard_range_covers_everything_once():
             spans = [shard_range(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_flat_adam_has_no_cpu_path():
+    """optim.FlatAdam re-homes CUDA parameters only: CPU parameters raise instead of falling back"""
+    import torch
+    from fira_icse_b200 import FiraLibraryError
+    from fira_icse_b200.optim import FlatAdam, cat_rows, grad_dest, mirror_of
+    p = torch.nn.Parameter(torch.zeros(8, 8))
+    with pytest.raises(FiraLibraryError):
+        FlatAdam([p], lr=1e-3)
+    # the lookups used by the backward passes treat ordinary tensors as "not re-homed"
+    assert mirror_of(p) is None and grad_dest((p,), (8, 8)) is None
+    assert torch.equal(cat_rows((p.data, p.data)), torch.cat((p.data, p.data), 0))
