@@ -73,13 +73,8 @@ def check(rc, what=""):
 LAUNCH_COUNT = 0     # C-ABI calls that enqueue GPU work (bench.py reports it as `gpu_launches`)
 
 
-SKIP_STREAMS = None  # experiment hook (tools only, FIRA_EXPERIMENT_SKIP_SIDE=1): cudaStream_t handles whose launches are dropped
-
-
 def call(name, *args):
     global LAUNCH_COUNT
-    if SKIP_STREAMS is not None and args and args[-1] in SKIP_STREAMS:
-        return               # timing experiment: how long is the step WITHOUT the side-stream work (results are garbage)
     LAUNCH_COUNT += 1
     check(getattr(lib(), name)(*args), name)
 

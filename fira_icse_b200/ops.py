@@ -302,8 +302,6 @@ class Fork:
         key = (device.index if device.index is not None else torch.cuda.current_device())
         if key not in _SIDE_STREAMS:
             _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(N_SIDE)]
-            if os.environ.get("FIRA_EXPERIMENT_SKIP_SIDE", "0") != "0":     # timing experiment only, see _lib.call
-                _lib.SKIP_STREAMS = {st.cuda_stream for st in _SIDE_STREAMS[key]}
         self.sides = _SIDE_STREAMS[key][:n_side] if n_side else _SIDE_STREAMS[key]
         self.side = self.sides[0]
         self.keep = []

@@ -6,12 +6,12 @@ timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r2l_p
 b() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --skip-parity-mode > gpurun_out/r2l_bench_$name.json 2> gpurun_out/r2l_bench_$name.err; }
 b default X=1
 b no_gemm_ln FIRA_GEMM_LN=0
-b skip_side FIRA_EXPERIMENT_SKIP_SIDE=1
+# (run L also timed the step with every side-stream launch dropped through a temporary hook, removed since: 2.58 ms)
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2l_bench_full.json 2> gpurun_out/r2l_bench_full.err
 for f in gpurun_out/r2l_pytest_*.log; do echo "== $f"; tail -n 14 $f; done
 python - <<'PY'
 import json
-for n in ['default','no_gemm_ln','skip_side','full']:
+for n in ['default','no_gemm_ln','full']:
     try:
         for l in open(f'gpurun_out/r2l_bench_{n}.json'):
             if l.startswith('{'):
