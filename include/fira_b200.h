@@ -243,7 +243,8 @@ int fira_copy_scores_packed_bwd(const void* src_proj, const void* tgt_proj, cons
                                 float* d_w_res, float* d_b_res, int B, int T_len, int S, int dim, int dtype, void* stream);
 
 /* ---- dual-copy mixture, loss and argmax (Model.py:54-86).  stats: 8 floats per row
- *      (vmax, vsum, cmax, csum, g0, g1, p_label, 0).  argmax_out may be NULL (training). */
+ *      (vmax, vsum, cmax, csum, g0, g1, p_label, 0).  argmax_out may be NULL (training).
+ *      logits / d_logits: 16-byte aligned, ld_logits a multiple of 8 (rows are read / written 8 elements at a time). */
 int fira_pointer_mix_nll_fwd(const void* logits, long ld_logits, const float* copy_scores, const float* gate_logits,
                              const unsigned char* mem_mask, const int* label, float* stats, float* nll,
                              int* argmax_out, long rows, int T_len, int V, int S, int dtype, void* stream);
