@@ -275,7 +275,7 @@ __global__ void comb_gate_bwd_kernel(const T* __restrict__ qk, long ld_qk, const
                                      const uint64_t* __restrict__ seed_ctr, uint32_t stream_id) {
   pdl_wait(); pdl_trigger();       // PDL (common.cuh)
   if (seed_ctr) seed += *seed_ctr;
-  __shared__ float red[ROWS_PER_CTA][4][D + 8];
+  __shared__ __align__(16) float red[ROWS_PER_CTA][4][D + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dv[4][8];
 #pragma unroll
@@ -313,12 +313,20 @@ __global__ void comb_gate_bwd_kernel(const T* __restrict__ qk, long ld_qk, const
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[warp][c][lane * 8 + i] = dv[c][i];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 4 * D; idx += CTA) {
-    const int c = idx / D, col = idx % D;
-    float s = 0.f;
+  {   // 4 x 256 sums of this CTA -> global: one 16-byte vector reduction per thread (256 threads x 4 columns)
+    const int c = threadIdx.x / (D / 4), col = (threadIdx.x % (D / 4)) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < ROWS_PER_CTA; ++w) s += red[w][c][col];
-    atomicAdd(d_vtab + c * D + col, s);
+    for (int w = 0; w < ROWS_PER_CTA; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(&red[w][c][col]);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* dst = d_vtab + c * D + col;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      atomicAdd(reinterpret_cast<float4*>(dst), s);
+    } else {
+      atomicAdd(dst, s.x); atomicAdd(dst + 1, s.y); atomicAdd(dst + 2, s.z); atomicAdd(dst + 3, s.w);
+    }
   }
 }
 
