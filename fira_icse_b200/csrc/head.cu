@@ -39,28 +39,44 @@ __global__ void __launch_bounds__(256) copy_scores_fwd_kernel(const T* __restric
   const float b_res = *b_res_p;
   __shared__ __align__(16) float tg[TMAX][D];
   __shared__ __align__(16) float wr[D];
+  __shared__ int active_t[TMAX];
+  __shared__ int n_active;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int idx = threadIdx.x; idx < Tn * D; idx += blockDim.x) tg[idx / D][idx % D] = Act<T>::ld(tgt + (long)b * Tn * D + idx);
+  const int rows_per_cta = 32;
+  const int s0 = blockIdx.x * rows_per_cta;
+  const int s_end = min(S, s0 + rows_per_cta);
+  // target rows that need scores (training: only rows whose label is a copy label).  The others get their zeros by
+  // ROW segments (one 128-byte store per warp and row) instead of one scattered 4-byte store per (source row, target row)
+  // out of the compute loop -- ~27 of 30 target rows of a commit are inactive.
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int t = 0; t < Tn; ++t) if (!row_mask || row_mask[(long)b * Tn + t]) active_t[n++] = t;
+    n_active = n;
+  }
   for (int idx = threadIdx.x; idx < D; idx += blockDim.x) wr[idx] = w_res[idx];
+  __syncthreads();
+  const int na = n_active;
+  for (int idx = threadIdx.x; idx < na * D; idx += blockDim.x) {
+    const int t = active_t[idx / D];
+    tg[t][idx % D] = Act<T>::ld(tgt + ((long)b * Tn + t) * D + idx % D);
+  }
+  if (row_mask)
+    for (int t = warp; t < Tn; t += 8)
+      if (row_mask[(long)b * Tn + t] == 0 && s0 + lane < s_end) sc[((long)b * Tn + t) * S + s0 + lane] = 0.f;
   __syncthreads();
   float w[8];
   Act<float>::load8(wr + lane * 8, w);
-  const int rows_per_cta = 32;
-  const int s_end = min(S, (int)(blockIdx.x + 1) * rows_per_cta);
-  for (int s = blockIdx.x * rows_per_cta + warp; s < s_end; s += 8) {
+  for (int s = s0 + warp; s < s_end; s += 8) {
     const long srow = src_row(ranges, b, S, s);
     if (srow < 0 || (src_mask && src_mask[(long)b * S + s] == 0)) {
-      for (int t = lane; t < Tn; t += 32) sc[((long)b * Tn + t) * S + s] = 0.f;
+      for (int a = lane; a < na; a += 32) sc[((long)b * Tn + active_t[a]) * S + s] = 0.f;
       continue;
     }
     float x[8];
     Act<T>::load8(src + srow * D + lane * 8, x);
-    for (int t = 0; t < Tn; ++t) {
-      if (row_mask && row_mask[(long)b * Tn + t] == 0) {          // warp-uniform
-        if (lane == 0) sc[((long)b * Tn + t) * S + s] = 0.f;
-        continue;
-      }
+    for (int a = 0; a < na; ++a) {
+      const int t = active_t[a];
       float y[8];
       Act<float>::load8(&tg[t][lane * 8], y);
       float acc = 0.f;
