@@ -452,9 +452,10 @@ class EncoderFn(torch.autograd.Function):
         else:
             call("fira_embed_nodes_fwd", _ptr(sou), _ptr(sub_token), _ptr(ast_change), _ptr(emb), _ptr(ast_emb),
                  _ptr(pos_table), _ptr(Xc), _ptr(Gin), B, n_code, n_sub, n_ast, D, pr.code, st)
-        # bf16 mode: the GCN layer is ONE fused kernel (gather -> tcgen05 -> LayerNorm epilogue, csrc/gcn_fused.cu);
-        # FIRA_GCN_FUSED=0 keeps the three-launch sequence (scatter, GEMM, LayerNorm) for A/B measurements
-        fused = pr.bf16 and os.environ.get("FIRA_GCN_FUSED", "0") != "0"      # TODO default on once validated on the GPU
+        # GCN layer: scatter (fira_gcn_aggregate) -> tcgen05 GEMM -> LayerNorm.  FIRA_GCN_FUSED=1 (bf16 mode) runs the whole
+        # layer as ONE kernel instead (gather -> tcgen05 -> LayerNorm epilogue, csrc/gcn_fused.cu): validated, but measured
+        # 33 us against 22 us for the three launches on the packed rows of a 64-commit batch, so it is opt-in
+        fused = pr.bf16 and os.environ.get("FIRA_GCN_FUSED", "0") != "0"
         rs = None if fused else edges.rowsum(n_code, n_sub, n_ast)
         erows = edges.rows_csr(n_code, n_sub, n_ast) if fused else None
         saved = []
