@@ -90,6 +90,31 @@ def cat_rows(ts):
     return torch.cat(ts, 0)
 
 
+def plan_layout(params, groups=()):
+    """Offsets (in elements) of `params` inside one flat buffer and the buffer length: the members of every group whose
+    parameters are all present lie back to back, in the group's order; every group / ungrouped tensor starts on an
+    ALIGN-element boundary; the length is a multiple of ALIGN.  Pure host logic (works on any tensors)."""
+    mine = {id(p) for p in params}
+    order, seen = [], set()
+    for grp in groups:                                   # adjacency groups first, members back to back
+        if all(id(p) in mine for p in grp) and not any(id(p) in seen for p in grp):
+            order.append(list(grp))
+            seen.update(id(p) for p in grp)
+    for p in params:
+        if id(p) not in seen:
+            order.append([p])
+            seen.add(id(p))
+    offs, off = {}, 0
+    for grp in order:
+        off = (off + ALIGN - 1) // ALIGN * ALIGN
+        for p in grp:
+            if len(grp) > 1 and p.numel() % 8:
+                raise ValueError("FlatAdam: grouped parameters must have a multiple of 8 elements")
+            offs[id(p)] = off
+            off += p.numel()
+    return [offs[id(p)] for p in params], (off + ALIGN - 1) // ALIGN * ALIGN
+
+
 class FlatAdam:
     """torch.optim.Adam(params, lr, betas, eps) on flat buffers; `step()` is one kernel launch (capturable)."""
 
@@ -101,25 +126,7 @@ class FlatAdam:
         if dev.type != "cuda":
             raise _lib.FiraLibraryError("FlatAdam: parameters must live on a CUDA device (no CPU path)")
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
-        mine = {id(p) for p in self.params}
-        order, seen = [], set()
-        for grp in groups:                                   # adjacency groups first, members back to back
-            if all(id(p) in mine for p in grp) and not any(id(p) in seen for p in grp):
-                order.append(list(grp))
-                seen.update(id(p) for p in grp)
-        for p in self.params:
-            if id(p) not in seen:
-                order.append([p])
-                seen.add(id(p))
-        offs, off = {}, 0
-        for grp in order:
-            off = (off + ALIGN - 1) // ALIGN * ALIGN
-            for p in grp:
-                if len(grp) > 1 and p.numel() % 8:
-                    raise ValueError("FlatAdam: grouped parameters must have a multiple of 8 elements")
-                offs[id(p)] = off
-                off += p.numel()
-        self.n = (off + ALIGN - 1) // ALIGN * ALIGN
+        self.offsets, self.n = plan_layout(self.params, groups)
         f32 = dict(dtype=torch.float32, device=dev)
         self.p = torch.zeros(self.n, **f32)
         self.g = torch.zeros(self.n, **f32)
@@ -131,7 +138,6 @@ class FlatAdam:
         self.fresh = False                                    # the bf16 mirror equals the parameters
         self.direct = False                                   # g is zero-filled and may be written by backward passes
         self.handed = set()
-        self.offsets = [offs[id(p)] for p in self.params]
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 view = self.p[o:o + p.numel()].view(p.shape)

@@ -165,3 +165,48 @@ def test_flat_adam_has_no_cpu_path():
     # the lookups used by the backward passes treat ordinary tensors as "not re-homed"
     assert mirror_of(p) is None and grad_dest((p,), (8, 8)) is None
     assert torch.equal(cat_rows((p.data, p.data)), torch.cat((p.data, p.data), 0))
+
+
+def test_flat_layout_keeps_fused_operands_adjacent():
+    """optim.plan_layout on the real parameter set: every group of TransModel.flat_groups() lies back to back (the q|k,
+    q|k|v and 12-way k|v weights / biases and every LayerNorm (weight, bias) pair are single views for ops.py), every
+    tensor starts on a 64-element boundary unless it continues a group, nothing overlaps, and the live parameters are
+    exactly the ones that receive gradients (264 of the 338)."""
+    from fira_testlib import seeded_model
+    from fira_icse_b200.optim import ALIGN, plan_layout
+    m = seeded_model()
+    params = [p for p in m.live_parameters() if p.requires_grad]
+    groups = m.flat_groups()
+    offs, n = plan_layout(params, groups)
+    off = {id(p): o for p, o in zip(params, offs)}
+    assert len(params) == 264 and n % ALIGN == 0
+    spans = sorted((o, o + p.numel()) for p, o in zip(params, offs))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= n
+    in_group = set()
+    for g in groups:
+        assert off[id(g[0])] % ALIGN == 0
+        for a, b in zip(g, g[1:]):
+            assert off[id(b)] == off[id(a)] + a.numel()
+            in_group.add(id(b))
+    assert all(off[id(p)] % ALIGN == 0 for p in params if id(p) not in in_group)
+    # the groups ops.py relies on
+    dec, enc = m.decoder, m.encoder
+    kv = [t for c in dec.cross_attention_list for t in (c.fc_k.weight, c.fc_v.weight)]
+    assert off[id(kv[-1])] - off[id(kv[0])] == 11 * 256 * 256
+    a0 = dec.attention_list[0]
+    assert off[id(a0.fc_v.weight)] == off[id(a0.fc_q.weight)] + 2 * 256 * 256
+    c0 = enc.combination_list2[0].linear_layers
+    assert off[id(c0[1].bias)] == off[id(c0[0].bias)] + 256
+    # two optimizers (head/decoder | encoder): groups split cleanly, none straddles the cut
+    dec_ids = {id(p) for p in list(m.decoder.parameters()) + list(m.out_fc.parameters()) + list(m.copy_net.parameters())}
+    pa = [p for p in params if id(p) in dec_ids]
+    pb = [p for p in params if id(p) not in dec_ids]
+    for part in (pa, pb):
+        o2, _ = plan_layout(part, groups)
+        o2 = {id(p): o for p, o in zip(part, o2)}
+        for g in groups:
+            if all(id(p) in o2 for p in g):
+                for a, b in zip(g, g[1:]):
+                    assert o2[id(b)] == o2[id(a)] + a.numel()
+            else:
+                assert not any(id(p) in o2 for p in g)
