@@ -210,3 +210,26 @@ def test_flat_layout_keeps_fused_operands_adjacent():
                     assert o2[id(b)] == o2[id(a)] + a.numel()
             else:
                 assert not any(id(p) in o2 for p in g)
+
+
+def test_timeline_summary_splits_replays_evenly():
+    """tools/timeline_summary.py: a trace of n identical graph replays is cut by kernel count even when a gap inside a
+    step is longer than the gaps between steps (the case that broke the gap heuristic)"""
+    import io
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import timeline_summary as TS
+    ev, t = [], 0.0
+    for step in range(3):
+        for i, name in enumerate(["void a_kernel<int>(int)", "void b_kernel(float*)", "void a_kernel<int>(int)", "c_kernel()"]):
+            gap = 500.0 if i == 2 else 1.0                     # a long stall INSIDE every step
+            t += gap
+            ev.append({"name": name, "ts": t, "dur": 5.0, "cat": "kernel", "args": {"stream": 7 + (i % 2)}})
+            t += 5.0
+        t += 20.0                                              # the gap between steps is shorter than the stall
+    steps = TS.split_steps(ev, 3)
+    assert [len(s) for s in steps] == [4, 4, 4]
+    out = io.StringIO()
+    TS.summarize(steps[1], out=out)
+    text = out.getvalue()
+    assert "kernels 4" in text and "a_kernel<int>" in text

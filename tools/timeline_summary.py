@@ -19,7 +19,15 @@ def short(name):
 
 
 def split_steps(ev, n_steps):
-    """the trace holds n_steps identical replays: cut at the largest inter-kernel gaps"""
+    """The trace holds n_steps replays of the same CUDA graph, separated by device synchronisations: the same number of
+    kernels each, so the sorted list is cut evenly when the per-chunk kernel-name counts agree; otherwise (an eager run
+    with shape-dependent launches) at the largest inter-kernel gaps."""
+    if n_steps > 1 and len(ev) % n_steps == 0:
+        k = len(ev) // n_steps
+        chunks = [ev[i * k:(i + 1) * k] for i in range(n_steps)]
+        names = [collections.Counter(short(e["name"]) for e in c) for c in chunks]
+        if all(n == names[0] for n in names[1:]):
+            return chunks
     gaps = sorted(((ev[i + 1]["ts"] - (ev[i]["ts"] + ev[i]["dur"]), i) for i in range(len(ev) - 1)), reverse=True)
     cuts = sorted(i for _, i in gaps[:n_steps - 1])
     out, lo = [], 0
